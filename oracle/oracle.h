@@ -1,0 +1,116 @@
+/*
+ * oracle/oracle.h -- CPU restatement of swift-png's hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may link or call this.  The product (swift-png_b200/) never does.
+ *
+ * Parity status: PINNED.  Decode is pinned by the reference's 161 PngSuite goldens
+ * (Sources/PNGIntegrationTests/Inputs/Common/ *.png <-> RGBA/ *.png.rgba), its gzip fixtures
+ * and zlib cross-checks; encode is pinned byte-for-byte by the reference's committed level-9
+ * outputs (Tests/Outputs/ *.png) and its gzip fixtures (levels 10 and 13); see
+ * tests/test_oracle_*.py.  The reference itself is Swift and no Swift toolchain exists in the
+ * image, so it cannot be compiled into oracle/_ref.
+ *
+ * Every function cites the reference file:line it restates (paths relative to the
+ * reference checkout).
+ */
+#ifndef PNGB200_ORACLE_H
+#define PNGB200_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes shared with include/pngb200.h (same numbering) */
+enum {
+    ORC_OK                                   = 0,
+    ORC_NEED_MORE_INPUT                      = 1,
+    /* LZ77.DecompressionError (Sources/LZ77/Inflator/LZ77.DecompressionError.swift:19-60) */
+    ORC_ERR_STREAM_CHECKSUM                  = -1,
+    ORC_ERR_BLOCK_TYPE                       = -2,
+    ORC_ERR_BLOCK_COUNT_PARITY               = -3,
+    ORC_ERR_RUNLITERAL_SYMBOL_COUNT          = -4,
+    ORC_ERR_CODELENGTH_HUFFMAN_TABLE         = -5,
+    ORC_ERR_CODELENGTH_SEQUENCE              = -6,
+    ORC_ERR_HUFFMAN_TABLE                    = -7,
+    ORC_ERR_STRING_REFERENCE                 = -8,
+    /* stricter than the reference: symbols the reference maps to padding rows */
+    ORC_ERR_INVALID_SYMBOL                   = -9,
+    /* LZ77.StreamHeaderError (Sources/LZ77/Inflator/LZ77.StreamHeaderError.swift:5-28) */
+    ORC_ERR_ZLIB_METHOD                      = -16,
+    ORC_ERR_ZLIB_WINDOW                      = -17,
+    ORC_ERR_ZLIB_CHECK_BITS                  = -18,
+    ORC_ERR_ZLIB_DICTIONARY                  = -19,
+    /* Gzip.StreamHeaderError (Sources/LZ77/Gzip/Gzip.StreamHeaderError.swift) */
+    ORC_ERR_GZIP_SIGIL                       = -32,
+    ORC_ERR_GZIP_METHOD                      = -33,
+    ORC_ERR_GZIP_FLAG_BITS                   = -34,
+    ORC_ERR_GZIP_HEADER_CHECKSUM_UNSUPPORTED = -35,
+    /* PNG.DecodingError cases raised by PNG.Decoder / PNG.Context */
+    ORC_ERR_PNG_EXTRANEOUS_IMAGE_DATA        = -48,
+    ORC_ERR_PNG_EXTRANEOUS_COMPRESSED_DATA   = -49,
+    ORC_ERR_PNG_INCOMPLETE_DATASTREAM        = -50,
+    /* API-level */
+    ORC_ERR_OUTPUT_CAPACITY                  = -64,
+    ORC_ERR_BAD_ARGUMENT                     = -65
+};
+
+enum { ORC_FORMAT_ZLIB = 0, ORC_FORMAT_IOS = 1, ORC_FORMAT_GZIP = 2 };
+
+typedef struct {
+    int32_t  status;
+    uint32_t a, b;          /* error payload (declared/computed checksum, bad code, ...) */
+    uint64_t consumed_bits; /* bit cursor when the call returned */
+    uint64_t produced;      /* bytes written to `out` */
+    uint32_t checksum;      /* Adler-32 (zlib/ios) or CRC-32 (gzip) of the output */
+    uint32_t blocks;        /* number of DEFLATE blocks seen */
+} orc_inflate_result;
+
+/* One-shot LZ77.Inflator / Gzip.Inflator: push(all of `in`) then pull().
+ * `out` may be NULL with cap 0 to measure; otherwise ORC_ERR_OUTPUT_CAPACITY if it overflows. */
+void orc_inflate(int format, const uint8_t* in, size_t n, uint8_t* out, size_t cap,
+                 orc_inflate_result* res);
+
+uint32_t orc_adler32(uint32_t adler, const uint8_t* p, size_t n);
+uint32_t orc_crc32(uint32_t crc, const uint8_t* p, size_t n);
+
+/* PNG.Decoder.defilter (Sources/PNG/Decoding/PNG.Decoder.swift:152-196).  `line` and `last`
+ * are pitch+1 bytes (filter byte first); in place. */
+void orc_defilter(uint8_t* line, const uint8_t* last, size_t count, int delay);
+uint8_t orc_paeth(uint8_t a, uint8_t b, uint8_t c);
+
+/* PNG.Decoder.push over a complete filtered stream + PNG.Image.assign
+ * (PNG.Decoder.swift:47-149, PNG.Image.swift:186-285).  `filtered` is the inflated IDAT stream.
+ * volume = bits per pixel (PNG.Format.Pixel.volume); depth = bits per sample (only used to pick
+ * the sub-byte expansion).  storage = w*h*((volume+7)>>3) bytes.  Returns ORC_OK,
+ * ORC_ERR_PNG_EXTRANEOUS_IMAGE_DATA or ORC_NEED_MORE_INPUT (too few rows). */
+int orc_png_unfilter(const uint8_t* filtered, size_t n, uint32_t w, uint32_t h, int volume,
+                     int depth, int interlaced, uint8_t* storage);
+
+/* whole PNG.Decoder path: inflate + unfilter + assign */
+int orc_png_decode(int format, const uint8_t* idat, size_t n, uint32_t w, uint32_t h, int volume,
+                   int depth, int interlaced, uint8_t* storage, orc_inflate_result* res);
+
+/* PNG.Encoder.filter (Sources/PNG/Encoding/PNG.Encoder.swift:132-204): choose + apply; writes
+ * pitch+1 bytes to `out`; `line`/`last` are pitch+1 bytes with a dummy byte 0. */
+void orc_filter_row(const uint8_t* line, const uint8_t* last, size_t count, int delay,
+                    uint8_t* out);
+/* PNG.Image.collect + Encoder.filter over a whole image: storage -> filtered stream
+ * (h*(pitch+1) bytes for non-interlaced; sum over passes for Adam7). returns bytes written */
+size_t orc_png_filter(const uint8_t* storage, uint32_t w, uint32_t h, int volume, int depth,
+                      int interlaced, uint8_t* filtered, size_t cap);
+size_t orc_png_filtered_size(uint32_t w, uint32_t h, int volume, int interlaced);
+
+/* LZ77.Deflator / Gzip.Deflator one-shot: push(in, last: true) then concatenated pull()s.
+ * Returns bytes written or (size_t)-1 on capacity overflow. */
+size_t orc_deflate(int format, int level, int exponent, const uint8_t* in, size_t n,
+                   uint8_t* out, size_t cap);
+size_t orc_deflate_bound(size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

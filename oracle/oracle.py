@@ -1,0 +1,173 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU restatement of swift-png's hot path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+ZLIB, IOS, GZIP = 0, 1, 2
+
+OK = 0
+NEED_MORE_INPUT = 1
+ERR_STREAM_CHECKSUM = -1
+ERR_BLOCK_TYPE = -2
+ERR_BLOCK_COUNT_PARITY = -3
+ERR_RUNLITERAL_SYMBOL_COUNT = -4
+ERR_CODELENGTH_HUFFMAN_TABLE = -5
+ERR_CODELENGTH_SEQUENCE = -6
+ERR_HUFFMAN_TABLE = -7
+ERR_STRING_REFERENCE = -8
+ERR_INVALID_SYMBOL = -9
+ERR_ZLIB_METHOD = -16
+ERR_ZLIB_WINDOW = -17
+ERR_ZLIB_CHECK_BITS = -18
+ERR_ZLIB_DICTIONARY = -19
+ERR_GZIP_SIGIL = -32
+ERR_GZIP_METHOD = -33
+ERR_GZIP_FLAG_BITS = -34
+ERR_GZIP_HEADER_CHECKSUM_UNSUPPORTED = -35
+ERR_PNG_EXTRANEOUS_IMAGE_DATA = -48
+ERR_PNG_EXTRANEOUS_COMPRESSED_DATA = -49
+ERR_PNG_INCOMPLETE_DATASTREAM = -50
+ERR_OUTPUT_CAPACITY = -64
+
+
+class InflateResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32),
+        ("a", C.c_uint32),
+        ("b", C.c_uint32),
+        ("consumed_bits", C.c_uint64),
+        ("produced", C.c_uint64),
+        ("checksum", C.c_uint32),
+        ("blocks", C.c_uint32),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/*.c into oracle/liboracle.so (gcc; a second or two)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p = C.POINTER(C.c_uint8)
+        L.orc_inflate.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                  C.POINTER(InflateResult)]
+        L.orc_inflate.restype = None
+        L.orc_adler32.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t]
+        L.orc_adler32.restype = C.c_uint32
+        L.orc_crc32.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t]
+        L.orc_crc32.restype = C.c_uint32
+        L.orc_paeth.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8]
+        L.orc_paeth.restype = C.c_uint8
+        L.orc_defilter.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int]
+        L.orc_defilter.restype = None
+        L.orc_png_unfilter.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p]
+        L.orc_png_unfilter.restype = C.c_int
+        L.orc_png_decode.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32,
+                                     C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.POINTER(InflateResult)]
+        L.orc_png_decode.restype = C.c_int
+        L.orc_filter_row.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.orc_filter_row.restype = None
+        L.orc_png_filter.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_size_t]
+        L.orc_png_filter.restype = C.c_size_t
+        L.orc_png_filtered_size.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+        L.orc_png_filtered_size.restype = C.c_size_t
+        if hasattr(L, "orc_deflate"):
+            L.orc_deflate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t,
+                                      C.c_void_p, C.c_size_t]
+            L.orc_deflate.restype = C.c_size_t
+            L.orc_deflate_bound.argtypes = [C.c_size_t]
+            L.orc_deflate_bound.restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+def inflate(data: bytes, fmt: int = ZLIB, cap: int | None = None):
+    """LZ77.Inflator / Gzip.Inflator one-shot.  Returns (status, bytes, InflateResult)."""
+    L = lib()
+    res = InflateResult()
+    if cap is None:
+        L.orc_inflate(fmt, data, len(data), None, 0, C.byref(res))  # measure
+        cap = int(res.produced)
+        res = InflateResult()
+    buf = C.create_string_buffer(max(cap, 1))
+    L.orc_inflate(fmt, data, len(data), buf, cap, C.byref(res))
+    return res.status, buf.raw[: res.produced], res
+
+
+def adler32(data: bytes, start: int = 1) -> int:
+    return lib().orc_adler32(start, data, len(data))
+
+
+def crc32(data: bytes, start: int = 0) -> int:
+    return lib().orc_crc32(start, data, len(data))
+
+
+def filtered_size(w: int, h: int, volume: int, interlaced: bool = False) -> int:
+    return lib().orc_png_filtered_size(w, h, volume, int(interlaced))
+
+
+def storage_size(w: int, h: int, volume: int) -> int:
+    return w * h * ((volume + 7) >> 3)
+
+
+def png_unfilter(filtered: bytes, w: int, h: int, volume: int, depth: int,
+                 interlaced: bool = False):
+    buf = C.create_string_buffer(max(storage_size(w, h, volume), 1))
+    st = lib().orc_png_unfilter(filtered, len(filtered), w, h, volume, depth, int(interlaced), buf)
+    return st, buf.raw[: storage_size(w, h, volume)]
+
+
+def png_decode(idat: bytes, w: int, h: int, volume: int, depth: int, interlaced: bool = False,
+               fmt: int = ZLIB):
+    """PNG.Decoder path: inflate + unfilter + assign.  Returns (status, storage, InflateResult)."""
+    buf = C.create_string_buffer(max(storage_size(w, h, volume), 1))
+    res = InflateResult()
+    st = lib().orc_png_decode(fmt, idat, len(idat), w, h, volume, depth, int(interlaced), buf,
+                              C.byref(res))
+    return st, buf.raw[: storage_size(w, h, volume)], res
+
+
+def png_filter(storage: bytes, w: int, h: int, volume: int, depth: int,
+               interlaced: bool = False) -> bytes:
+    """PNG.Encoder filter-select over an image: storage -> filtered stream."""
+    n = filtered_size(w, h, volume, interlaced)
+    buf = C.create_string_buffer(max(n, 1))
+    got = lib().orc_png_filter(storage, w, h, volume, depth, int(interlaced), buf, n)
+    assert got == n, (got, n)
+    return buf.raw[:n]
+
+
+def deflate(data: bytes, level: int = 9, fmt: int = ZLIB, exponent: int = 15) -> bytes:
+    """LZ77.Deflator / Gzip.Deflator one-shot."""
+    L = lib()
+    cap = L.orc_deflate_bound(len(data))
+    buf = C.create_string_buffer(cap)
+    n = L.orc_deflate(fmt, level, exponent, data, len(data), buf, cap)
+    assert n != C.c_size_t(-1).value
+    return buf.raw[:n]
