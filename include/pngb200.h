@@ -1,0 +1,185 @@
+/*
+ * pngb200.h -- C ABI of the B200-native PNG hot path (DEFLATE inflate + scanline unfilter, and
+ * the encode-side mirrors), the drop-in boundary for swift-png's `PNG.Decoder` / `PNG.Encoder`
+ * / `LZ77.Inflator` / `LZ77.Deflator` call sites.
+ *
+ * swift-png has no FFI of its own: its hot path sits behind internal Swift value types.  The
+ * entry points below are what a Swift `CPNGB200` system-library target would bind (see
+ * INTEGRATION.md for the module map and the replacement bodies).  Each one cites the reference
+ * interface it replaces (paths relative to the swift-png checkout).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns a
+ * pngb200_status; nothing throws or aborts.  Per-item results (status + payload mirroring the
+ * Swift error enums' associated values) are written into the descriptor arrays.
+ * A pngb200_ctx is bound to one CUDA device and owns one CUDA stream plus grow-only device
+ * workspaces; it must be used by one thread at a time (same rule as the Swift structs).
+ * There is NO CPU fallback: if CUDA is unavailable pngb200_ctx_create fails.
+ */
+#ifndef PNGB200_H
+#define PNGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNGB200_VERSION 1
+
+/* ---- status codes (negative = error).  The numbering is shared with oracle/oracle.h ---- */
+typedef enum pngb200_status {
+    PNGB200_OK                                   = 0,  /* stream complete (push returned nil) */
+    PNGB200_NEED_MORE_INPUT                      = 1,  /* push returned () : truncated stream */
+    /* LZ77.DecompressionError, Sources/LZ77/Inflator/LZ77.DecompressionError.swift:19-60 */
+    PNGB200_ERR_STREAM_CHECKSUM                  = -1, /* payload a=declared b=computed */
+    PNGB200_ERR_BLOCK_TYPE                       = -2, /* a=code */
+    PNGB200_ERR_BLOCK_COUNT_PARITY               = -3, /* a=LEN b=NLEN */
+    PNGB200_ERR_RUNLITERAL_SYMBOL_COUNT          = -4, /* a=count */
+    PNGB200_ERR_CODELENGTH_HUFFMAN_TABLE         = -5,
+    PNGB200_ERR_CODELENGTH_SEQUENCE              = -6,
+    PNGB200_ERR_HUFFMAN_TABLE                    = -7,
+    PNGB200_ERR_STRING_REFERENCE                 = -8,
+    PNGB200_ERR_INVALID_SYMBOL                   = -9, /* stricter than the reference, see DESIGN.md */
+    /* LZ77.StreamHeaderError, Sources/LZ77/Inflator/LZ77.StreamHeaderError.swift:5-28 */
+    PNGB200_ERR_ZLIB_METHOD                      = -16, /* a=code */
+    PNGB200_ERR_ZLIB_WINDOW                      = -17, /* a=exponent */
+    PNGB200_ERR_ZLIB_CHECK_BITS                  = -18,
+    PNGB200_ERR_ZLIB_DICTIONARY                  = -19,
+    /* Gzip.StreamHeaderError, Sources/LZ77/Gzip/Gzip.StreamHeaderError.swift */
+    PNGB200_ERR_GZIP_SIGIL                       = -32,
+    PNGB200_ERR_GZIP_METHOD                      = -33, /* a=code */
+    PNGB200_ERR_GZIP_FLAG_BITS                   = -34, /* a=flags */
+    PNGB200_ERR_GZIP_HEADER_CHECKSUM_UNSUPPORTED = -35,
+    /* PNG.DecodingError cases raised on this path, Sources/PNG/Decoding/PNG.Decoder.swift:51-55,
+     * :142-147 and PNG.Context.swift:134-141 */
+    PNGB200_ERR_PNG_EXTRANEOUS_IMAGE_DATA        = -48,
+    PNGB200_ERR_PNG_EXTRANEOUS_COMPRESSED_DATA   = -49,
+    PNGB200_ERR_PNG_INCOMPLETE_DATASTREAM        = -50,
+    /* API-level */
+    PNGB200_ERR_OUTPUT_CAPACITY                  = -64,
+    PNGB200_ERR_BAD_ARGUMENT                     = -65,
+    PNGB200_ERR_CUDA                             = -66, /* see pngb200_last_error */
+    PNGB200_ERR_INTERNAL                         = -67
+} pngb200_status;
+
+/* LZ77.Format (.zlib, .ios) + Gzip.Format, Sources/LZ77/Wrappers/LZ77.Format.swift:8-12 */
+typedef enum pngb200_format { PNGB200_FORMAT_ZLIB = 0, PNGB200_FORMAT_IOS = 1, PNGB200_FORMAT_GZIP = 2 } pngb200_format;
+
+/* where the data pointers of a batch live */
+typedef enum pngb200_memspace {
+    PNGB200_MEM_HOST   = 0, /* host pointers (pinned or pageable); copies are part of the call */
+    PNGB200_MEM_DEVICE = 1  /* device pointers on the context's GPU; nothing is copied */
+} pngb200_memspace;
+
+/* ---- context ---- */
+typedef struct pngb200_ctx pngb200_ctx;
+
+/* device < 0: the calling thread's current CUDA device.  Returns NULL on failure (no GPU, no
+ * sm_100 device, out of memory); pngb200_last_error(NULL) then describes why. */
+pngb200_ctx* pngb200_ctx_create(int device);
+void         pngb200_ctx_destroy(pngb200_ctx* ctx);
+const char*  pngb200_last_error(const pngb200_ctx* ctx);
+/* the cudaStream_t all of this context's work is enqueued on (for event timing / interop) */
+void*        pngb200_ctx_stream(pngb200_ctx* ctx);
+int          pngb200_ctx_device(const pngb200_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t     pngb200_ctx_launch_count(const pngb200_ctx* ctx);
+/* tuning knob: 0 = automatic, 1 = force the one-warp-per-stream inflate kernel,
+ * 2 = force the block-parallel inflate kernel */
+void         pngb200_ctx_set_inflate_mode(pngb200_ctx* ctx, int mode);
+
+/* ---- batched one-shot entry points (the throughput path) ---- */
+
+/* One standalone DEFLATE stream: LZ77.Inflator(format:).push(all); pull()  /  Gzip.extract.
+ * Replaces Sources/LZ77/Inflator/LZ77.Inflator.swift:30-61 and Sources/LZ77/Gzip/Gzip.swift:6-11. */
+typedef struct pngb200_stream_desc {
+    const uint8_t* src;       /* compressed stream */
+    size_t         src_len;
+    uint8_t*       dst;       /* inflated bytes */
+    size_t         dst_cap;
+    int32_t        format;    /* pngb200_format */
+    /* results */
+    int32_t        status;    /* pngb200_status */
+    uint32_t       err_a, err_b;
+    uint32_t       checksum;  /* Adler-32 (zlib, ios) or CRC-32 (gzip) of the output */
+    uint32_t       blocks;    /* DEFLATE blocks decoded */
+    uint64_t       produced;  /* bytes written to dst */
+    uint64_t       consumed_bits;
+} pngb200_stream_desc;
+
+int pngb200_inflate_batch(pngb200_ctx* ctx, pngb200_stream_desc* streams, size_t count, int memspace);
+
+/* One PNG image's IDAT stream: PNG.Decoder.push(data, size:, pixel:, delegate: image.assign)
+ * over the concatenated IDAT payload.  Replaces Sources/PNG/Decoding/PNG.Decoder.swift:47-149
+ * (+ defilter :152-196, PNG.paeth PNG.swift:124-147) and PNG.Image.assign
+ * (Sources/PNG/PNG.Image.swift:186-285).  `pixels` receives PNG.Image.storage exactly:
+ * width*height*((volume+7)>>3) bytes, row-major, 16-bit samples big-endian, sub-byte depths
+ * expanded to one byte per pixel. */
+typedef struct pngb200_image_desc {
+    const uint8_t* idat;      /* concatenated IDAT payloads (a zlib stream; raw DEFLATE for .ios) */
+    size_t         idat_len;
+    uint8_t*       pixels;
+    size_t         pixels_cap;
+    uint32_t       width, height;
+    uint8_t        volume;    /* bits per pixel, PNG.Format.Pixel.volume */
+    uint8_t        depth;     /* bits per sample */
+    uint8_t        interlaced;
+    uint8_t        format;    /* PNGB200_FORMAT_ZLIB (PNG.Standard.common) or _IOS */
+    /* results */
+    int32_t        status;
+    uint32_t       err_a, err_b;
+    uint32_t       checksum;  /* Adler-32 of the filtered stream */
+    uint32_t       blocks;
+    uint64_t       produced;  /* inflated (filtered) bytes */
+} pngb200_image_desc;
+
+int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* images, size_t count, int memspace);
+/* same, split so that device time can be bracketed with events: enqueue returns once all work is
+ * queued on pngb200_ctx_stream; finish synchronises and fills in the result fields. */
+int pngb200_decode_batch_enqueue(pngb200_ctx* ctx, pngb200_image_desc* images, size_t count, int memspace);
+int pngb200_decode_batch_finish(pngb200_ctx* ctx, pngb200_image_desc* images, size_t count);
+
+/* The unfilter stage alone (PNG.Decoder.defilter + PNG.Image.assign over an already inflated
+ * stream); `idat`/`idat_len` hold the FILTERED bytes.  Exposed for kernel-level tests/benchmarks. */
+int pngb200_unfilter_batch(pngb200_ctx* ctx, pngb200_image_desc* images, size_t count, int memspace);
+
+/* Encode-side stage 1: PNG.Image.collect + PNG.Encoder.filter for every row
+ * (Sources/PNG/Encoding/PNG.Encoder.swift:132-204,230-234; PNG.Image.swift:431-544).
+ * `pixels` is the INPUT (PNG.Image.storage), `idat`... see pngb200_filter_desc. */
+typedef struct pngb200_filter_desc {
+    const uint8_t* pixels;    /* PNG.Image.storage */
+    size_t         pixels_len;
+    uint8_t*       filtered;  /* out: height*(pitch+1) bytes (sum over Adam7 passes if interlaced) */
+    size_t         filtered_cap;
+    uint32_t       width, height;
+    uint8_t        volume, depth, interlaced, reserved;
+    int32_t        status;
+    uint64_t       produced;
+} pngb200_filter_desc;
+
+int pngb200_filter_batch(pngb200_ctx* ctx, pngb200_filter_desc* images, size_t count, int memspace);
+
+/* size helpers (host arithmetic only) */
+size_t pngb200_filtered_size(uint32_t width, uint32_t height, int volume, int interlaced);
+size_t pngb200_storage_size(uint32_t width, uint32_t height, int volume);
+
+/* ---- streaming handles (LZ77.Inflator value-type semantics, layered on the batch path) ---- */
+typedef struct pngb200_inflator pngb200_inflator;
+/* LZ77.Inflator.init(format:) / Gzip.Inflator.init(), LZ77.Inflator.swift:18-23 */
+pngb200_inflator* pngb200_inflator_create(pngb200_ctx* ctx, int format);
+void              pngb200_inflator_destroy(pngb200_inflator* z);
+/* push(_:) : copies `data`; returns PNGB200_OK when the stream is complete (Swift: nil),
+ * PNGB200_NEED_MORE_INPUT when it wants more (Swift: ()), <0 on error (Swift: throws). */
+int    pngb200_inflator_push(pngb200_inflator* z, const uint8_t* data, size_t n);
+/* pull(_ count:) : exactly `count` bytes or PNGB200_NEED_MORE_INPUT (Swift: nil) */
+int    pngb200_inflator_pull(pngb200_inflator* z, uint8_t* dst, size_t count);
+/* pull() : everything available; returns the number of bytes copied (<= cap) */
+size_t pngb200_inflator_pull_all(pngb200_inflator* z, uint8_t* dst, size_t cap);
+size_t pngb200_inflator_available(const pngb200_inflator* z);
+void   pngb200_inflator_error(const pngb200_inflator* z, int* status, uint32_t* a, uint32_t* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNGB200_H */

@@ -168,8 +168,11 @@ int orc_png_decode(int format, const uint8_t* idat, size_t n, uint32_t w, uint32
     if (st == ORC_OK || st == ORC_NEED_MORE_INPUT) {
         int u = orc_png_unfilter(filtered, (size_t)res->produced, w, h, volume, depth, interlaced,
                                  storage);
+        /* a complete stream with too few rows is NOT an error in the reference: Decoder.push
+         * returns `continue` == nil and the IEND check (PNG.Context.swift:134-141) passes; the
+         * missing rows of `storage` are simply never assigned. */
         if (u == ORC_ERR_PNG_EXTRANEOUS_IMAGE_DATA) st = u;
-        else if (st == ORC_NEED_MORE_INPUT || u == ORC_NEED_MORE_INPUT)
+        else if (st == ORC_NEED_MORE_INPUT)
             st = ORC_ERR_PNG_INCOMPLETE_DATASTREAM; /* PNG.Context.swift:134-141 at IEND */
     }
     free(filtered);

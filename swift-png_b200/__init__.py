@@ -1,0 +1,372 @@
+"""swift-png_b200: B200-native PNG hot path (DEFLATE inflate + scanline unfilter, filter-select)
+behind swift-png's `PNG.Decoder` / `PNG.Encoder` / `LZ77.Inflator` interface.
+
+This module is the thin host-side binding of the C ABI in include/pngb200.h (ctypes; the
+library itself has no Python or torch dependency).  It mirrors the reference's names:
+
+    LZ77.Inflator(format:).push/pull      -> Inflator(ctx, format).push / .pull / .pull_all
+    Gzip.extract(from:)                   -> gzip_extract(ctx, data)
+    PNG.Decoder.push + PNG.Image.assign   -> decode_batch(ctx, [ImageJob...])
+    PNG.Encoder.filter (+ collect)        -> filter_batch(ctx, [...])
+
+There is NO CPU fallback: importing works anywhere (so the symbol table can be checked without a
+GPU) but creating a Context raises unless an sm_100 GPU and the in-tree libpngb200.so exist.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import importlib.util
+import os
+from dataclasses import dataclass
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpngb200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "pngb200.h")
+
+# pngb200_status
+OK = 0
+NEED_MORE_INPUT = 1
+ERR_STREAM_CHECKSUM = -1
+ERR_BLOCK_TYPE = -2
+ERR_BLOCK_COUNT_PARITY = -3
+ERR_RUNLITERAL_SYMBOL_COUNT = -4
+ERR_CODELENGTH_HUFFMAN_TABLE = -5
+ERR_CODELENGTH_SEQUENCE = -6
+ERR_HUFFMAN_TABLE = -7
+ERR_STRING_REFERENCE = -8
+ERR_INVALID_SYMBOL = -9
+ERR_ZLIB_METHOD = -16
+ERR_ZLIB_WINDOW = -17
+ERR_ZLIB_CHECK_BITS = -18
+ERR_ZLIB_DICTIONARY = -19
+ERR_GZIP_SIGIL = -32
+ERR_GZIP_METHOD = -33
+ERR_GZIP_FLAG_BITS = -34
+ERR_GZIP_HEADER_CHECKSUM_UNSUPPORTED = -35
+ERR_PNG_EXTRANEOUS_IMAGE_DATA = -48
+ERR_PNG_EXTRANEOUS_COMPRESSED_DATA = -49
+ERR_PNG_INCOMPLETE_DATASTREAM = -50
+ERR_OUTPUT_CAPACITY = -64
+ERR_BAD_ARGUMENT = -65
+ERR_CUDA = -66
+ERR_INTERNAL = -67
+
+FORMAT_ZLIB, FORMAT_IOS, FORMAT_GZIP = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+
+
+class StreamDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src_len", C.c_size_t),
+        ("dst", C.c_void_p), ("dst_cap", C.c_size_t),
+        ("format", C.c_int32),
+        ("status", C.c_int32), ("err_a", C.c_uint32), ("err_b", C.c_uint32),
+        ("checksum", C.c_uint32), ("blocks", C.c_uint32),
+        ("produced", C.c_uint64), ("consumed_bits", C.c_uint64),
+    ]
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [
+        ("idat", C.c_void_p), ("idat_len", C.c_size_t),
+        ("pixels", C.c_void_p), ("pixels_cap", C.c_size_t),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("volume", C.c_uint8), ("depth", C.c_uint8), ("interlaced", C.c_uint8), ("format", C.c_uint8),
+        ("status", C.c_int32), ("err_a", C.c_uint32), ("err_b", C.c_uint32),
+        ("checksum", C.c_uint32), ("blocks", C.c_uint32),
+        ("produced", C.c_uint64),
+    ]
+
+
+class FilterDesc(C.Structure):
+    _fields_ = [
+        ("pixels", C.c_void_p), ("pixels_len", C.c_size_t),
+        ("filtered", C.c_void_p), ("filtered_cap", C.c_size_t),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("volume", C.c_uint8), ("depth", C.c_uint8), ("interlaced", C.c_uint8), ("reserved", C.c_uint8),
+        ("status", C.c_int32), ("produced", C.c_uint64),
+    ]
+
+
+class PNGB200Error(RuntimeError):
+    def __init__(self, status: int, message: str = ""):
+        super().__init__(f"pngb200 status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree (nvcc, sm_100a).  Works without a GPU."""
+    spec = importlib.util.spec_from_file_location("_pngb200_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)
+
+
+def lib():
+    """Load libpngb200.so (raises if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PNGB200Error(ERR_CUDA, f"{LIB_PATH} is missing: run `python __graft_entry__.py build`; "
+                           "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.pngb200_ctx_create.argtypes = [C.c_int]
+    L.pngb200_ctx_create.restype = C.c_void_p
+    L.pngb200_ctx_destroy.argtypes = [C.c_void_p]
+    L.pngb200_ctx_destroy.restype = None
+    L.pngb200_last_error.argtypes = [C.c_void_p]
+    L.pngb200_last_error.restype = C.c_char_p
+    L.pngb200_ctx_stream.argtypes = [C.c_void_p]
+    L.pngb200_ctx_stream.restype = C.c_void_p
+    L.pngb200_ctx_device.argtypes = [C.c_void_p]
+    L.pngb200_ctx_device.restype = C.c_int
+    L.pngb200_ctx_launch_count.argtypes = [C.c_void_p]
+    L.pngb200_ctx_launch_count.restype = C.c_uint64
+    L.pngb200_ctx_set_inflate_mode.argtypes = [C.c_void_p, C.c_int]
+    L.pngb200_ctx_set_inflate_mode.restype = None
+    L.pngb200_inflate_batch.argtypes = [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_int]
+    L.pngb200_inflate_batch.restype = C.c_int
+    for name in ("pngb200_decode_batch", "pngb200_decode_batch_enqueue", "pngb200_unfilter_batch"):
+        getattr(L, name).argtypes = [C.c_void_p, C.POINTER(ImageDesc), C.c_size_t, C.c_int]
+        getattr(L, name).restype = C.c_int
+    L.pngb200_decode_batch_finish.argtypes = [C.c_void_p, C.POINTER(ImageDesc), C.c_size_t]
+    L.pngb200_decode_batch_finish.restype = C.c_int
+    L.pngb200_filter_batch.argtypes = [C.c_void_p, C.POINTER(FilterDesc), C.c_size_t, C.c_int]
+    L.pngb200_filter_batch.restype = C.c_int
+    L.pngb200_filtered_size.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+    L.pngb200_filtered_size.restype = C.c_size_t
+    L.pngb200_storage_size.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.pngb200_storage_size.restype = C.c_size_t
+    L.pngb200_inflator_create.argtypes = [C.c_void_p, C.c_int]
+    L.pngb200_inflator_create.restype = C.c_void_p
+    L.pngb200_inflator_destroy.argtypes = [C.c_void_p]
+    L.pngb200_inflator_destroy.restype = None
+    L.pngb200_inflator_push.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.pngb200_inflator_push.restype = C.c_int
+    L.pngb200_inflator_pull.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pngb200_inflator_pull.restype = C.c_int
+    L.pngb200_inflator_pull_all.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pngb200_inflator_pull_all.restype = C.c_size_t
+    L.pngb200_inflator_available.argtypes = [C.c_void_p]
+    L.pngb200_inflator_available.restype = C.c_size_t
+    L.pngb200_inflator_error.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint32),
+                                         C.POINTER(C.c_uint32)]
+    L.pngb200_inflator_error.restype = None
+    _lib = L
+    return L
+
+
+def filtered_size(w: int, h: int, volume: int, interlaced: bool = False) -> int:
+    return lib().pngb200_filtered_size(w, h, volume, int(interlaced))
+
+
+def storage_size(w: int, h: int, volume: int) -> int:
+    return lib().pngb200_storage_size(w, h, volume)
+
+
+class Context:
+    """One GPU: a CUDA stream plus grow-only workspaces (pngb200_ctx)."""
+
+    def __init__(self, device: int = -1):
+        self._lib = lib()
+        self.handle = self._lib.pngb200_ctx_create(device)
+        if not self.handle:
+            raise PNGB200Error(ERR_CUDA, self._lib.pngb200_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.pngb200_ctx_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def stream(self) -> int:
+        return self._lib.pngb200_ctx_stream(self.handle) or 0
+
+    @property
+    def device(self) -> int:
+        return self._lib.pngb200_ctx_device(self.handle)
+
+    @property
+    def launches(self) -> int:
+        return self._lib.pngb200_ctx_launch_count(self.handle)
+
+    def set_inflate_mode(self, mode: int):
+        self._lib.pngb200_ctx_set_inflate_mode(self.handle, mode)
+
+    def check(self, rc: int):
+        if rc != OK:
+            raise PNGB200Error(rc, self._lib.pngb200_last_error(self.handle).decode())
+
+
+@dataclass
+class DecodedImage:
+    status: int
+    pixels: bytes
+    checksum: int
+    produced: int
+    blocks: int
+    err_a: int = 0
+    err_b: int = 0
+
+
+def _buf_addr(b) -> int:
+    return C.addressof(b)
+
+
+def inflate_batch(ctx: Context, streams, fmt: int = FORMAT_ZLIB, caps=None):
+    """LZ77.Inflator one-shot over a batch of host byte strings.
+    Returns a list of (status, bytes, StreamDesc)."""
+    n = len(streams)
+    descs = (StreamDesc * n)()
+    keep = []
+    for i, s in enumerate(streams):
+        cap = caps[i] if caps is not None else max(len(s) * 1100 + 1024, 1024)
+        src = C.create_string_buffer(bytes(s), len(s)) if len(s) else C.create_string_buffer(1)
+        dst = C.create_string_buffer(max(cap, 1))
+        keep.append((src, dst))
+        descs[i].src = _buf_addr(src)
+        descs[i].src_len = len(s)
+        descs[i].dst = _buf_addr(dst)
+        descs[i].dst_cap = cap
+        descs[i].format = fmt if isinstance(fmt, int) else fmt[i]
+    ctx.check(ctx._lib.pngb200_inflate_batch(ctx.handle, descs, n, MEM_HOST))
+    return [(descs[i].status, keep[i][1].raw[: descs[i].produced], descs[i]) for i in range(n)]
+
+
+def gzip_extract(ctx: Context, data: bytes, cap: int | None = None) -> bytes:
+    """Gzip.extract(from:)"""
+    (st, out, d), = inflate_batch(ctx, [data], FORMAT_GZIP, None if cap is None else [cap])
+    if st != OK:
+        raise PNGB200Error(st, "gzip_extract")
+    return out
+
+
+def decode_batch(ctx: Context, images, memspace: int = MEM_HOST):
+    """PNG.Decoder over a batch.  `images`: iterable of dicts/objects with
+    idat (bytes), width, height, volume, depth, interlaced, fmt.  Host memory path."""
+    images = list(images)
+    n = len(images)
+    descs = (ImageDesc * n)()
+    keep = []
+    for i, im in enumerate(images):
+        g = im if isinstance(im, dict) else im.__dict__
+        idat = bytes(g["idat"])
+        w, h, vol = g["width"], g["height"], g["volume"]
+        size = storage_size(w, h, vol)
+        src = C.create_string_buffer(idat, len(idat)) if len(idat) else C.create_string_buffer(1)
+        dst = C.create_string_buffer(max(size, 1))
+        keep.append((src, dst, size))
+        descs[i].idat = _buf_addr(src)
+        descs[i].idat_len = len(idat)
+        descs[i].pixels = _buf_addr(dst)
+        descs[i].pixels_cap = size
+        descs[i].width, descs[i].height = w, h
+        descs[i].volume, descs[i].depth = vol, g["depth"]
+        descs[i].interlaced = int(bool(g.get("interlaced", False)))
+        descs[i].format = g.get("fmt", FORMAT_ZLIB)
+    ctx.check(ctx._lib.pngb200_decode_batch(ctx.handle, descs, n, memspace))
+    return [DecodedImage(descs[i].status, keep[i][1].raw[: keep[i][2]], descs[i].checksum,
+                         descs[i].produced, descs[i].blocks, descs[i].err_a, descs[i].err_b)
+            for i in range(n)]
+
+
+def unfilter_batch(ctx: Context, images):
+    """PNG.Decoder.defilter + PNG.Image.assign over already inflated streams
+    (`filtered` bytes per image).  Returns list of (status, pixels)."""
+    images = list(images)
+    n = len(images)
+    descs = (ImageDesc * n)()
+    keep = []
+    for i, g in enumerate(images):
+        f = bytes(g["filtered"])
+        w, h, vol = g["width"], g["height"], g["volume"]
+        size = storage_size(w, h, vol)
+        src = C.create_string_buffer(f, len(f)) if len(f) else C.create_string_buffer(1)
+        dst = C.create_string_buffer(max(size, 1))
+        keep.append((src, dst, size))
+        descs[i].idat = _buf_addr(src)
+        descs[i].idat_len = len(f)
+        descs[i].pixels = _buf_addr(dst)
+        descs[i].pixels_cap = size
+        descs[i].width, descs[i].height = w, h
+        descs[i].volume, descs[i].depth = vol, g["depth"]
+        descs[i].interlaced = int(bool(g.get("interlaced", False)))
+    ctx.check(ctx._lib.pngb200_unfilter_batch(ctx.handle, descs, n, MEM_HOST))
+    return [(descs[i].status, keep[i][1].raw[: keep[i][2]]) for i in range(n)]
+
+
+def filter_batch(ctx: Context, images):
+    """PNG.Image.collect + PNG.Encoder.filter over a batch of storages.  Returns list of bytes."""
+    images = list(images)
+    n = len(images)
+    descs = (FilterDesc * n)()
+    keep = []
+    for i, g in enumerate(images):
+        px = bytes(g["pixels"])
+        w, h, vol = g["width"], g["height"], g["volume"]
+        il = bool(g.get("interlaced", False))
+        fsz = filtered_size(w, h, vol, il)
+        src = C.create_string_buffer(px, len(px))
+        dst = C.create_string_buffer(max(fsz, 1))
+        keep.append((src, dst, fsz))
+        descs[i].pixels = _buf_addr(src)
+        descs[i].pixels_len = len(px)
+        descs[i].filtered = _buf_addr(dst)
+        descs[i].filtered_cap = fsz
+        descs[i].width, descs[i].height = w, h
+        descs[i].volume, descs[i].depth, descs[i].interlaced = vol, g["depth"], int(il)
+    ctx.check(ctx._lib.pngb200_filter_batch(ctx.handle, descs, n, MEM_HOST))
+    return [keep[i][1].raw[: keep[i][2]] for i in range(n)]
+
+
+class Inflator:
+    """LZ77.Inflator / Gzip.Inflator value semantics over the GPU path (streaming push/pull)."""
+
+    def __init__(self, ctx: Context, fmt: int = FORMAT_ZLIB):
+        self.ctx = ctx
+        self.handle = ctx._lib.pngb200_inflator_create(ctx.handle, fmt)
+        if not self.handle:
+            raise PNGB200Error(ERR_BAD_ARGUMENT, "inflator_create")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx._lib.pngb200_inflator_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def push(self, data: bytes) -> int:
+        """Returns OK when the stream is complete (Swift: nil), NEED_MORE_INPUT otherwise;
+        raises PNGB200Error on a decompression error (Swift: throws)."""
+        st = self.ctx._lib.pngb200_inflator_push(self.handle, bytes(data), len(data))
+        if st < 0:
+            a, b, s = C.c_uint32(), C.c_uint32(), C.c_int()
+            self.ctx._lib.pngb200_inflator_error(self.handle, C.byref(s), C.byref(a), C.byref(b))
+            e = PNGB200Error(st, self.ctx._lib.pngb200_last_error(self.ctx.handle).decode())
+            e.payload = (a.value, b.value)
+            raise e
+        return st
+
+    def pull(self, count: int):
+        """Exactly `count` bytes or None (Swift: pull(_:) -> [UInt8]?)."""
+        buf = C.create_string_buffer(max(count, 1))
+        st = self.ctx._lib.pngb200_inflator_pull(self.handle, buf, count)
+        return buf.raw[:count] if st == OK else None
+
+    def pull_all(self) -> bytes:
+        n = self.ctx._lib.pngb200_inflator_available(self.handle)
+        buf = C.create_string_buffer(max(n, 1))
+        got = self.ctx._lib.pngb200_inflator_pull_all(self.handle, buf, n)
+        return buf.raw[:got]

@@ -1,0 +1,832 @@
+// pngb200_api.cu -- the C ABI declared in include/pngb200.h: contexts, batching, host glue.
+//
+// The library talks to the CUDA runtime directly (no torch types anywhere); callers that live in
+// a PyTorch process pass raw device pointers (tensor.data_ptr()) with PNGB200_MEM_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "checksum.cuh"
+#include "common.cuh"
+#include "filter.cuh"
+#include "inflate_serial.cuh"
+#include "unfilter.cuh"
+
+using namespace pngb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct DevBuf {
+    void*  p   = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(n + n / 4, (size_t)1 << 16);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            want = n;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+struct PinBuf {
+    void*  p   = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max(n + n / 4, (size_t)1 << 12);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+const int ADAM7[7][4] = {{0, 0, 3, 3}, {4, 0, 3, 3}, {0, 4, 2, 3}, {2, 0, 2, 2},
+                         {0, 2, 1, 2}, {1, 0, 1, 1}, {0, 1, 0, 1}};
+
+}  // namespace
+
+struct pngb200_ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t     launches = 0;
+    int          inflate_mode = 0;
+    int          sm_count = 148;
+    std::string  error;
+    bool         pending = false;
+    int          pending_memspace = 0;
+    // device workspaces (grow-only)
+    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_par;
+    // pinned host tables
+    PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc;
+    // geometry of the pending decode batch
+    std::vector<uint64_t> expected;   // filtered bytes expected per image
+    std::vector<size_t>   out_offset; // staging offsets (HOST memspace)
+    std::vector<size_t>   out_bytes;
+};
+
+namespace {
+
+int set_error(pngb200_ctx* ctx, int code, const char* fmt, ...)
+{
+    char    buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return set_error(ctx, PNGB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call,               \
+                             cudaGetErrorString(e_), __FILE__, __LINE__);                         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- inflate (+ checksum) over a device-resident job table ----
+// h_jobs: host copy (for dst_cap based chunk layout); d_jobs/d_results device arrays of `count`.
+int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
+{
+    StreamJob*    d_jobs    = ctx->d_jobs.as<StreamJob>();
+    StreamResult* d_results = ctx->d_results.as<StreamResult>();
+    CU(cudaMemsetAsync(d_results, 0, sizeof(StreamResult) * count, ctx->stream));
+    inflate_serial_kernel<<<(unsigned)count, 32, 0, ctx->stream>>>(d_jobs, d_results, (int)count);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    // checksum: chunk layout from dst_cap (an upper bound of `produced`)
+    CU(ctx->h_misc.reserve(sizeof(uint32_t) * (count + 1)));
+    uint32_t* base = ctx->h_misc.as<uint32_t>();
+    uint64_t  total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        base[i] = (uint32_t)total;
+        total += (h_jobs[i].dst_cap + CK_CHUNK - 1) / CK_CHUNK;
+    }
+    base[count] = (uint32_t)total;
+    if (total >= (1ull << 31)) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "batch too large");
+    CU(ctx->d_misc.reserve(sizeof(uint32_t) * (count + 1)));
+    CU(ctx->d_partial.reserve(sizeof(uint64_t) * 2 * std::max<uint64_t>(total, 1)));
+    CU(cudaMemcpyAsync(ctx->d_misc.p, base, sizeof(uint32_t) * (count + 1), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    ChecksumParams cp;
+    cp.jobs = d_jobs;
+    cp.results = d_results;
+    cp.chunk_base = ctx->d_misc.as<uint32_t>();
+    cp.partial = ctx->d_partial.as<uint64_t>();
+    cp.count = (uint32_t)count;
+    cp.total_chunks = (uint32_t)total;
+    if (total) {
+        checksum_chunk_kernel<<<(unsigned)total, CK_THREADS, 0, ctx->stream>>>(cp);
+        ctx->launches++;
+    }
+    checksum_fold_kernel<<<(unsigned)count, 32, 0, ctx->stream>>>(cp);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return PNGB200_OK;
+}
+
+struct Geometry {
+    uint64_t filtered;  // total filtered bytes
+    uint64_t storage;
+    uint32_t pitch;     // non-interlaced pitch
+    uint8_t  bpp;
+    bool     fast;      // eligible for the wavefront kernel
+};
+
+bool geometry(uint32_t w, uint32_t h, int volume, int depth, int interlaced, Geometry* g)
+{
+    if (w == 0 || h == 0 || volume <= 0 || volume > 64 || depth <= 0 || depth > 16) return false;
+    g->filtered = pngb200_filtered_size(w, h, volume, interlaced);
+    g->storage  = pngb200_storage_size(w, h, volume);
+    g->pitch    = (uint32_t)(((uint64_t)w * volume + 7) >> 3);
+    g->bpp      = (uint8_t)((volume + 7) >> 3);
+    g->fast     = !interlaced && depth >= 8 &&
+              (g->bpp == 1 || g->bpp == 2 || g->bpp == 3 || g->bpp == 4 || g->bpp == 6 || g->bpp == 8);
+    return true;
+}
+
+// unfilter stage over device-resident filtered streams
+struct UnfilterItem {
+    const uint8_t*      filtered;
+    uint8_t*            filtered_mut;  // same buffer when the library owns it, else null
+    uint8_t*            pixels;
+    const StreamResult* inflated;
+    uint64_t            filtered_len;
+    uint32_t            w, h;
+    uint8_t             volume, depth, interlaced;
+    Geometry            g;
+};
+
+int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
+{
+    std::vector<ImageJob>   fast;
+    std::vector<GenericJob> slow;
+    std::vector<uint32_t>   band_base;
+    uint64_t                bands = 0;
+    for (const UnfilterItem& it : items) {
+        if (it.g.fast) {
+            ImageJob j;
+            j.filtered = it.filtered;
+            j.pixels = it.pixels;
+            j.inflated = it.inflated;
+            j.filtered_len = it.filtered_len;
+            j.width = it.w;
+            j.height = it.h;
+            j.pitch = it.g.pitch;
+            j.volume = it.volume;
+            j.depth = it.depth;
+            j.interlaced = 0;
+            j.bpp = it.g.bpp;
+            fast.push_back(j);
+            band_base.push_back((uint32_t)bands);
+            bands += (it.h + 31) / 32;
+        } else {
+            GenericJob j;
+            j.filtered = it.filtered_mut;
+            j.pixels = it.pixels;
+            j.inflated = it.inflated;
+            j.filtered_len = it.filtered_len;
+            j.width = it.w;
+            j.height = it.h;
+            j.volume = it.volume;
+            j.depth = it.depth;
+            j.interlaced = it.interlaced;
+            j.bpp = it.g.bpp;
+            slow.push_back(j);
+        }
+    }
+    band_base.push_back((uint32_t)bands);
+    if (bands >= (1ull << 31)) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "batch too large");
+    if (!fast.empty()) {
+        size_t jb = sizeof(ImageJob) * fast.size(), bb = sizeof(uint32_t) * band_base.size();
+        size_t off_bb = align_up(jb, 256), off_pr = align_up(off_bb + bb, 256);
+        size_t total = off_pr + sizeof(uint32_t) * (bands + 1);
+        CU(ctx->h_imgjobs.reserve(off_pr));
+        CU(ctx->d_imgjobs.reserve(total));
+        memcpy(ctx->h_imgjobs.p, fast.data(), jb);
+        memcpy((char*)ctx->h_imgjobs.p + off_bb, band_base.data(), bb);
+        CU(cudaMemcpyAsync(ctx->d_imgjobs.p, ctx->h_imgjobs.p, off_pr, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync((char*)ctx->d_imgjobs.p + off_pr, 0, sizeof(uint32_t) * (bands + 1), ctx->stream));
+        WaveParams p;
+        p.jobs = ctx->d_imgjobs.as<ImageJob>();
+        p.band_base = (const uint32_t*)((char*)ctx->d_imgjobs.p + off_bb);
+        p.progress = (uint32_t*)((char*)ctx->d_imgjobs.p + off_pr);
+        p.ticket = p.progress + bands;
+        p.njobs = (uint32_t)fast.size();
+        p.total_bands = (uint32_t)bands;
+        unsigned grid = (unsigned)std::min<uint64_t>((bands + WAVE_WARPS - 1) / WAVE_WARPS,
+                                                     (uint64_t)ctx->sm_count * 8);
+        unfilter_wave_kernel<<<grid, WAVE_WARPS * 32, 0, ctx->stream>>>(p);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    if (!slow.empty()) {
+        size_t jb = sizeof(GenericJob) * slow.size();
+        CU(ctx->h_genjobs.reserve(jb));
+        CU(ctx->d_genjobs.reserve(jb));
+        memcpy(ctx->h_genjobs.p, slow.data(), jb);
+        CU(cudaMemcpyAsync(ctx->d_genjobs.p, ctx->h_genjobs.p, jb, cudaMemcpyHostToDevice, ctx->stream));
+        unfilter_generic_kernel<<<(unsigned)slow.size(), 128, 0, ctx->stream>>>(
+            ctx->d_genjobs.as<GenericJob>(), (int)slow.size());
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    return PNGB200_OK;
+}
+
+}  // namespace
+
+// ================================ C ABI ================================
+
+extern "C" {
+
+size_t pngb200_filtered_size(uint32_t w, uint32_t h, int volume, int interlaced)
+{
+    if (!interlaced) return (size_t)h * ((((size_t)w * (size_t)volume + 7) >> 3) + 1);
+    size_t total = 0;
+    for (int z = 0; z < 7; ++z) {
+        size_t sx = ((size_t)w + (1u << ADAM7[z][2]) - ADAM7[z][0] - 1) >> ADAM7[z][2];
+        size_t sy = ((size_t)h + (1u << ADAM7[z][3]) - ADAM7[z][1] - 1) >> ADAM7[z][3];
+        if (sx == 0 || sy == 0) continue;
+        total += sy * (((sx * (size_t)volume + 7) >> 3) + 1);
+    }
+    return total;
+}
+
+size_t pngb200_storage_size(uint32_t w, uint32_t h, int volume)
+{
+    return (size_t)w * (size_t)h * (size_t)((volume + 7) >> 3);
+}
+
+pngb200_ctx* pngb200_ctx_create(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= n) {
+        set_error(nullptr, PNGB200_ERR_BAD_ARGUMENT, "device %d out of range (%d devices)", device, n);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                  device, prop.major, prop.minor);
+        return nullptr;
+    }
+    pngb200_ctx* ctx = new pngb200_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    DeviceGuard guard(device);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "cudaStreamCreate failed");
+        delete ctx;
+        return nullptr;
+    }
+    return ctx;
+}
+
+void pngb200_ctx_destroy(pngb200_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->d_jobs, &ctx->d_results, &ctx->d_imgjobs, &ctx->d_genjobs, &ctx->d_misc,
+                      &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_par})
+        b->release();
+    for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc})
+        b->release();
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* pngb200_last_error(const pngb200_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
+void*       pngb200_ctx_stream(pngb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int         pngb200_ctx_device(const pngb200_ctx* ctx) { return ctx ? ctx->device : -1; }
+uint64_t    pngb200_ctx_launch_count(const pngb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void        pngb200_ctx_set_inflate_mode(pngb200_ctx* ctx, int mode) { if (ctx) ctx->inflate_mode = mode; }
+
+// ---------------- standalone inflate ----------------
+int pngb200_inflate_batch(pngb200_ctx* ctx, pngb200_stream_desc* s, size_t count, int memspace)
+{
+    if (!ctx || (!s && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is pending");
+    if (count == 0) return PNGB200_OK;
+    DeviceGuard guard(ctx->device);
+    CU(ctx->h_jobs.reserve(sizeof(StreamJob) * count));
+    CU(ctx->d_jobs.reserve(sizeof(StreamJob) * count));
+    CU(ctx->d_results.reserve(sizeof(StreamResult) * count));
+    CU(ctx->h_results.reserve(sizeof(StreamResult) * count));
+    StreamJob* jobs = ctx->h_jobs.as<StreamJob>();
+    std::vector<size_t> in_off(count), out_off(count);
+    size_t in_total = 0, out_total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        if ((!s[i].src && s[i].src_len) || (!s[i].dst && s[i].dst_cap) || s[i].format < 0 || s[i].format > 2)
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "stream %zu: bad descriptor", i);
+        in_off[i] = in_total;
+        out_off[i] = out_total;
+        in_total += align_up(s[i].src_len + 16, 256);
+        out_total += align_up(s[i].dst_cap + 16, 256);
+    }
+    if (memspace == PNGB200_MEM_HOST) {
+        CU(ctx->d_in.reserve(in_total));
+        CU(ctx->d_out.reserve(out_total));
+        for (size_t i = 0; i < count; ++i)
+            if (s[i].src_len)
+                CU(cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + in_off[i], s[i].src, s[i].src_len,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (size_t i = 0; i < count; ++i) {
+        bool host = memspace == PNGB200_MEM_HOST;
+        jobs[i].src = host ? ctx->d_in.as<uint8_t>() + in_off[i] : s[i].src;
+        jobs[i].src_len = s[i].src_len;
+        jobs[i].dst = host ? ctx->d_out.as<uint8_t>() + out_off[i] : s[i].dst;
+        jobs[i].dst_cap = s[i].dst_cap;
+        jobs[i].start_bit = 0;
+        jobs[i].start_out = 0;
+        jobs[i].format = s[i].format;
+        jobs[i].phase = 0;
+    }
+    CU(cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(StreamJob) * count, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = run_inflate(ctx, jobs, count);
+    if (rc != PNGB200_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, sizeof(StreamResult) * count,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const StreamResult* r = ctx->h_results.as<StreamResult>();
+    for (size_t i = 0; i < count; ++i) {
+        s[i].status = r[i].status;
+        s[i].err_a = r[i].err_a;
+        s[i].err_b = r[i].err_b;
+        s[i].checksum = r[i].checksum;
+        s[i].blocks = r[i].blocks;
+        s[i].produced = r[i].produced;
+        s[i].consumed_bits = r[i].consumed_bits;
+        if (memspace == PNGB200_MEM_HOST && r[i].produced)
+            CU(cudaMemcpyAsync(s[i].dst, ctx->d_out.as<uint8_t>() + out_off[i], r[i].produced,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PNGB200_OK;
+}
+
+// ---------------- PNG decode: inflate + unfilter ----------------
+int pngb200_decode_batch_enqueue(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)
+{
+    if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is already pending");
+    if (count == 0) return PNGB200_OK;
+    DeviceGuard guard(ctx->device);
+    const bool host = memspace == PNGB200_MEM_HOST;
+    std::vector<Geometry> geo(count);
+    std::vector<size_t>   f_off(count), in_off(count);
+    ctx->expected.assign(count, 0);
+    ctx->out_offset.assign(count, 0);
+    ctx->out_bytes.assign(count, 0);
+    size_t f_total = 0, in_total = 0, out_total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        if (!geometry(im[i].width, im[i].height, im[i].volume, im[i].depth, im[i].interlaced, &geo[i]) ||
+            (!im[i].idat && im[i].idat_len) || !im[i].pixels || im[i].format > 1)
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "image %zu: bad descriptor", i);
+        if (im[i].pixels_cap < geo[i].storage)
+            return set_error(ctx, PNGB200_ERR_OUTPUT_CAPACITY, "image %zu: pixels_cap %zu < %llu", i,
+                             im[i].pixels_cap, (unsigned long long)geo[i].storage);
+        ctx->expected[i] = geo[i].filtered;
+        f_off[i] = f_total;
+        f_total += align_up(geo[i].filtered + 64, 256);
+        in_off[i] = in_total;
+        in_total += align_up(im[i].idat_len + 16, 256);
+        ctx->out_offset[i] = out_total;
+        ctx->out_bytes[i] = geo[i].storage;
+        out_total += align_up(geo[i].storage + 16, 256);
+    }
+    CU(ctx->d_filtered.reserve(f_total));
+    CU(ctx->h_jobs.reserve(sizeof(StreamJob) * count));
+    CU(ctx->d_jobs.reserve(sizeof(StreamJob) * count));
+    CU(ctx->d_results.reserve(sizeof(StreamResult) * count));
+    CU(ctx->h_results.reserve(sizeof(StreamResult) * count));
+    if (host) {
+        CU(ctx->d_in.reserve(in_total));
+        CU(ctx->d_out.reserve(out_total));
+        for (size_t i = 0; i < count; ++i)
+            if (im[i].idat_len)
+                CU(cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + in_off[i], im[i].idat, im[i].idat_len,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    }
+    StreamJob* jobs = ctx->h_jobs.as<StreamJob>();
+    for (size_t i = 0; i < count; ++i) {
+        jobs[i].src = host ? ctx->d_in.as<uint8_t>() + in_off[i] : im[i].idat;
+        jobs[i].src_len = im[i].idat_len;
+        jobs[i].dst = ctx->d_filtered.as<uint8_t>() + f_off[i];
+        jobs[i].dst_cap = geo[i].filtered + 16;  // room to notice extraneous image data
+        jobs[i].start_bit = 0;
+        jobs[i].start_out = 0;
+        jobs[i].format = im[i].format;
+        jobs[i].phase = 0;
+    }
+    CU(cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(StreamJob) * count, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = run_inflate(ctx, jobs, count);
+    if (rc != PNGB200_OK) return rc;
+    std::vector<UnfilterItem> items(count);
+    for (size_t i = 0; i < count; ++i) {
+        UnfilterItem& it = items[i];
+        it.filtered = jobs[i].dst;
+        it.filtered_mut = jobs[i].dst;
+        it.pixels = host ? ctx->d_out.as<uint8_t>() + ctx->out_offset[i] : im[i].pixels;
+        it.inflated = ctx->d_results.as<StreamResult>() + i;
+        it.filtered_len = 0;
+        it.w = im[i].width;
+        it.h = im[i].height;
+        it.volume = im[i].volume;
+        it.depth = im[i].depth;
+        it.interlaced = im[i].interlaced;
+        it.g = geo[i];
+    }
+    rc = run_unfilter(ctx, items);
+    if (rc != PNGB200_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, sizeof(StreamResult) * count,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    if (host)
+        for (size_t i = 0; i < count; ++i)
+            CU(cudaMemcpyAsync(im[i].pixels, ctx->d_out.as<uint8_t>() + ctx->out_offset[i], ctx->out_bytes[i],
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->pending = true;
+    ctx->pending_memspace = memspace;
+    return PNGB200_OK;
+}
+
+int pngb200_decode_batch_finish(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count)
+{
+    if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (count == 0) return PNGB200_OK;
+    if (!ctx->pending || ctx->expected.size() != count)
+        return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "no matching pending decode batch");
+    DeviceGuard guard(ctx->device);
+    ctx->pending = false;
+    CU(cudaStreamSynchronize(ctx->stream));
+    const StreamResult* r = ctx->h_results.as<StreamResult>();
+    for (size_t i = 0; i < count; ++i) {
+        int st = r[i].status;
+        // PNG.Decoder.push / PNG.Context.push(ancillary: IEND) error mapping
+        if (st == PNGB200_ERR_OUTPUT_CAPACITY) st = PNGB200_ERR_PNG_EXTRANEOUS_IMAGE_DATA;
+        else if (st == PNGB200_NEED_MORE_INPUT) st = PNGB200_ERR_PNG_INCOMPLETE_DATASTREAM;
+        else if (st == PNGB200_OK && r[i].produced > ctx->expected[i]) st = PNGB200_ERR_PNG_EXTRANEOUS_IMAGE_DATA;
+        im[i].status = st;
+        im[i].err_a = r[i].err_a;
+        im[i].err_b = r[i].err_b;
+        im[i].checksum = r[i].checksum;
+        im[i].blocks = r[i].blocks;
+        im[i].produced = r[i].produced;
+    }
+    return PNGB200_OK;
+}
+
+int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)
+{
+    int rc = pngb200_decode_batch_enqueue(ctx, im, count, memspace);
+    if (rc != PNGB200_OK) return rc;
+    return pngb200_decode_batch_finish(ctx, im, count);
+}
+
+int pngb200_unfilter_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)
+{
+    if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is pending");
+    if (count == 0) return PNGB200_OK;
+    DeviceGuard guard(ctx->device);
+    const bool host = memspace == PNGB200_MEM_HOST;
+    std::vector<UnfilterItem> items(count);
+    std::vector<size_t>       f_off(count), o_off(count);
+    size_t f_total = 0, o_total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        UnfilterItem& it = items[i];
+        if (!geometry(im[i].width, im[i].height, im[i].volume, im[i].depth, im[i].interlaced, &it.g) ||
+            !im[i].idat || !im[i].pixels)
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "image %zu: bad descriptor", i);
+        if (im[i].pixels_cap < it.g.storage) return set_error(ctx, PNGB200_ERR_OUTPUT_CAPACITY, "image %zu: pixels_cap", i);
+        f_off[i] = f_total;
+        // the generic kernel reconstructs in place, so it always works on a private copy
+        if (host || !it.g.fast) f_total += align_up(im[i].idat_len + 64, 256);
+        o_off[i] = o_total;
+        o_total += align_up(it.g.storage + 16, 256);
+    }
+    CU(ctx->d_filtered.reserve(std::max<size_t>(f_total, 256)));
+    if (host) CU(ctx->d_out.reserve(o_total));
+    for (size_t i = 0; i < count; ++i) {
+        UnfilterItem& it = items[i];
+        uint8_t* priv = ctx->d_filtered.as<uint8_t>() + f_off[i];
+        if (host || !it.g.fast) {
+            CU(cudaMemcpyAsync(priv, im[i].idat, im[i].idat_len,
+                               host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+            it.filtered = priv;
+            it.filtered_mut = priv;
+        } else {
+            it.filtered = im[i].idat;
+            it.filtered_mut = nullptr;
+        }
+        it.pixels = host ? ctx->d_out.as<uint8_t>() + o_off[i] : im[i].pixels;
+        it.inflated = nullptr;
+        it.filtered_len = im[i].idat_len;
+        it.w = im[i].width;
+        it.h = im[i].height;
+        it.volume = im[i].volume;
+        it.depth = im[i].depth;
+        it.interlaced = im[i].interlaced;
+    }
+    int rc = run_unfilter(ctx, items);
+    if (rc != PNGB200_OK) return rc;
+    if (host)
+        for (size_t i = 0; i < count; ++i)
+            CU(cudaMemcpyAsync(im[i].pixels, ctx->d_out.as<uint8_t>() + o_off[i], items[i].g.storage,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < count; ++i) {
+        uint64_t expect = items[i].g.filtered;
+        im[i].produced = im[i].idat_len;
+        im[i].status = im[i].idat_len > expect ? PNGB200_ERR_PNG_EXTRANEOUS_IMAGE_DATA : PNGB200_OK;
+    }
+    return PNGB200_OK;
+}
+
+// ---------------- encode stage 1: filter select + apply ----------------
+int pngb200_filter_batch(pngb200_ctx* ctx, pngb200_filter_desc* im, size_t count, int memspace)
+{
+    if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is pending");
+    if (count == 0) return PNGB200_OK;
+    DeviceGuard guard(ctx->device);
+    const bool host = memspace == PNGB200_MEM_HOST;
+    std::vector<FilterJob> jobs(count);
+    std::vector<size_t>    p_off(count), f_off(count);
+    size_t p_total = 0, f_total = 0;
+    uint64_t rows = 0;
+    std::vector<uint32_t> row_base(count + 1);
+    for (size_t i = 0; i < count; ++i) {
+        Geometry g;
+        if (!geometry(im[i].width, im[i].height, im[i].volume, im[i].depth, im[i].interlaced, &g) ||
+            !im[i].pixels || !im[i].filtered)
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "image %zu: bad descriptor", i);
+        if (im[i].pixels_len < g.storage || im[i].filtered_cap < g.filtered)
+            return set_error(ctx, PNGB200_ERR_OUTPUT_CAPACITY, "image %zu: buffer too small", i);
+        p_off[i] = p_total;
+        f_off[i] = f_total;
+        p_total += align_up(g.storage + 16, 256);
+        f_total += align_up(g.filtered + 16, 256);
+        im[i].produced = g.filtered;
+        row_base[i] = (uint32_t)rows;
+        rows += filter_rows(im[i].width, im[i].height, im[i].interlaced);
+    }
+    row_base[count] = (uint32_t)rows;
+    if (rows >= (1ull << 31)) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "batch too large");
+    if (host) {
+        CU(ctx->d_in.reserve(p_total));
+        CU(ctx->d_out.reserve(f_total));
+        for (size_t i = 0; i < count; ++i)
+            CU(cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + p_off[i], im[i].pixels,
+                               pngb200_storage_size(im[i].width, im[i].height, im[i].volume),
+                               cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (size_t i = 0; i < count; ++i) {
+        jobs[i].pixels = host ? ctx->d_in.as<uint8_t>() + p_off[i] : im[i].pixels;
+        jobs[i].filtered = host ? ctx->d_out.as<uint8_t>() + f_off[i] : im[i].filtered;
+        jobs[i].width = im[i].width;
+        jobs[i].height = im[i].height;
+        jobs[i].volume = im[i].volume;
+        jobs[i].depth = im[i].depth;
+        jobs[i].interlaced = im[i].interlaced;
+        jobs[i].bpp = (uint8_t)((im[i].volume + 7) >> 3);
+    }
+    size_t jb = sizeof(FilterJob) * count, rb = sizeof(uint32_t) * (count + 1);
+    size_t off_rb = align_up(jb, 256);
+    CU(ctx->h_genjobs.reserve(off_rb + rb));
+    CU(ctx->d_genjobs.reserve(off_rb + rb));
+    memcpy(ctx->h_genjobs.p, jobs.data(), jb);
+    memcpy((char*)ctx->h_genjobs.p + off_rb, row_base.data(), rb);
+    CU(cudaMemcpyAsync(ctx->d_genjobs.p, ctx->h_genjobs.p, off_rb + rb, cudaMemcpyHostToDevice, ctx->stream));
+    filter_rows_kernel<<<(unsigned)std::max<uint64_t>(1, (rows + FILTER_WARPS - 1) / FILTER_WARPS),
+                         FILTER_WARPS * 32, 0, ctx->stream>>>(
+        ctx->d_genjobs.as<FilterJob>(), (const uint32_t*)((char*)ctx->d_genjobs.p + off_rb),
+        (uint32_t)count, (uint32_t)rows);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (host)
+        for (size_t i = 0; i < count; ++i)
+            CU(cudaMemcpyAsync(im[i].filtered, ctx->d_out.as<uint8_t>() + f_off[i], im[i].produced,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < count; ++i) im[i].status = PNGB200_OK;
+    return PNGB200_OK;
+}
+
+// ---------------- streaming inflator handle ----------------
+struct pngb200_inflator {
+    pngb200_ctx*         ctx;
+    int                  format;
+    std::vector<uint8_t> input;      // everything pushed so far
+    DevBuf               d_in, d_out, d_job, d_res, d_misc, d_partial;
+    PinBuf               h_res;
+    size_t               uploaded = 0;
+    uint64_t             resume_bit = 0, resume_out = 0, produced = 0, current = 0;
+    uint32_t             phase = 0;
+    bool                 terminal = false;
+    int                  status = PNGB200_NEED_MORE_INPUT;
+    uint32_t             err_a = 0, err_b = 0;
+};
+
+pngb200_inflator* pngb200_inflator_create(pngb200_ctx* ctx, int format)
+{
+    if (!ctx || format < 0 || format > 2) return nullptr;
+    pngb200_inflator* z = new pngb200_inflator();
+    z->ctx = ctx;
+    z->format = format;
+    return z;
+}
+
+void pngb200_inflator_destroy(pngb200_inflator* z)
+{
+    if (!z) return;
+    DeviceGuard guard(z->ctx->device);
+    cudaStreamSynchronize(z->ctx->stream);
+    for (DevBuf* b : {&z->d_in, &z->d_out, &z->d_job, &z->d_res, &z->d_misc, &z->d_partial}) b->release();
+    z->h_res.release();
+    delete z;
+}
+
+static int inflator_grow_out(pngb200_inflator* z, size_t need)
+{
+    pngb200_ctx* ctx = z->ctx;
+    if (need <= z->d_out.cap) return PNGB200_OK;
+    DevBuf bigger;
+    CU(bigger.reserve(std::max(need, z->d_out.cap * 2)));
+    if (z->produced) CU(cudaMemcpyAsync(bigger.p, z->d_out.p, z->produced, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    z->d_out.release();
+    z->d_out = bigger;
+    return PNGB200_OK;
+}
+
+int pngb200_inflator_push(pngb200_inflator* z, const uint8_t* data, size_t n)
+{
+    if (!z || (!data && n)) return PNGB200_ERR_BAD_ARGUMENT;
+    pngb200_ctx* ctx = z->ctx;
+    if (z->terminal) return PNGB200_OK;  // LZ77.Inflator ignores input after the terminal state
+    if (z->status < 0) return z->status;
+    DeviceGuard guard(ctx->device);
+    z->input.insert(z->input.end(), data, data + n);
+    // device copy of the whole input (grow-only; new bytes appended)
+    if (z->input.size() + 16 > z->d_in.cap) {
+        DevBuf bigger;
+        CU(bigger.reserve(z->input.size() * 2 + 4096));
+        z->d_in.release();
+        z->d_in = bigger;
+        z->uploaded = 0;
+    }
+    if (z->input.size() > z->uploaded)
+        CU(cudaMemcpyAsync(z->d_in.as<uint8_t>() + z->uploaded, z->input.data() + z->uploaded,
+                           z->input.size() - z->uploaded, cudaMemcpyHostToDevice, ctx->stream));
+    z->uploaded = z->input.size();
+    CU(z->d_job.reserve(sizeof(StreamJob)));
+    CU(z->d_res.reserve(sizeof(StreamResult)));
+    CU(z->h_res.reserve(sizeof(StreamResult) + sizeof(StreamJob)));
+    int rc = inflator_grow_out(z, std::max<size_t>(1 << 16, z->produced + 4 * n + 1024));
+    if (rc != PNGB200_OK) return rc;
+    for (;;) {
+        StreamJob* job = (StreamJob*)((char*)z->h_res.p + sizeof(StreamResult));
+        job->src = z->d_in.as<uint8_t>();
+        job->src_len = z->input.size();
+        job->dst = z->d_out.as<uint8_t>();
+        job->dst_cap = z->d_out.cap;
+        job->start_bit = z->resume_bit;
+        job->start_out = z->resume_out;
+        job->format = z->format;
+        job->phase = (int32_t)z->phase;
+        CU(cudaMemcpyAsync(z->d_job.p, job, sizeof(StreamJob), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(z->d_res.p, 0, sizeof(StreamResult), ctx->stream));
+        inflate_serial_kernel<<<1, 32, 0, ctx->stream>>>(z->d_job.as<StreamJob>(), z->d_res.as<StreamResult>(), 1);
+        ctx->launches++;
+        // checksum over everything produced so far (cheap relative to the inflate itself)
+        uint32_t base[2] = {0, (uint32_t)((z->d_out.cap + CK_CHUNK - 1) / CK_CHUNK)};
+        CU(z->d_misc.reserve(sizeof base));
+        CU(z->d_partial.reserve(sizeof(uint64_t) * 2 * std::max<uint32_t>(base[1], 1)));
+        CU(cudaMemcpyAsync(z->d_misc.p, base, sizeof base, cudaMemcpyHostToDevice, ctx->stream));
+        ChecksumParams cp;
+        cp.jobs = z->d_job.as<StreamJob>();
+        cp.results = z->d_res.as<StreamResult>();
+        cp.chunk_base = z->d_misc.as<uint32_t>();
+        cp.partial = z->d_partial.as<uint64_t>();
+        cp.count = 1;
+        cp.total_chunks = base[1];
+        checksum_chunk_kernel<<<base[1], CK_THREADS, 0, ctx->stream>>>(cp);
+        checksum_fold_kernel<<<1, 32, 0, ctx->stream>>>(cp);
+        ctx->launches += 2;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(z->h_res.p, z->d_res.p, sizeof(StreamResult), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        const StreamResult r = *z->h_res.as<StreamResult>();
+        // remember the last completed block boundary: the next run resumes there
+        z->phase = r.phase;
+        z->resume_bit = r.resume_bit;
+        z->resume_out = r.resume_out;
+        if (r.status == PNGB200_ERR_OUTPUT_CAPACITY) {
+            z->produced = r.resume_out;
+            rc = inflator_grow_out(z, z->d_out.cap * 2);
+            if (rc != PNGB200_OK) return rc;
+            continue;
+        }
+        z->produced = r.produced;
+        z->status = r.status;
+        z->err_a = r.err_a;
+        z->err_b = r.err_b;
+        if (r.status == PNGB200_OK) z->terminal = true;
+        return r.status;
+    }
+}
+
+size_t pngb200_inflator_available(const pngb200_inflator* z) { return z ? (size_t)(z->produced - z->current) : 0; }
+
+int pngb200_inflator_pull(pngb200_inflator* z, uint8_t* dst, size_t count)
+{
+    if (!z || (!dst && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (z->produced - z->current < count) return PNGB200_NEED_MORE_INPUT;
+    pngb200_ctx* ctx = z->ctx;
+    DeviceGuard guard(ctx->device);
+    if (count) {
+        CU(cudaMemcpyAsync(dst, z->d_out.as<uint8_t>() + z->current, count, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    z->current += count;
+    return PNGB200_OK;
+}
+
+size_t pngb200_inflator_pull_all(pngb200_inflator* z, uint8_t* dst, size_t cap)
+{
+    if (!z) return 0;
+    size_t n = std::min<size_t>(cap, (size_t)(z->produced - z->current));
+    if (pngb200_inflator_pull(z, dst, n) != PNGB200_OK) return 0;
+    return n;
+}
+
+void pngb200_inflator_error(const pngb200_inflator* z, int* status, uint32_t* a, uint32_t* b)
+{
+    if (!z) return;
+    if (status) *status = z->status;
+    if (a) *a = z->err_a;
+    if (b) *b = z->err_b;
+}
+
+}  // extern "C"

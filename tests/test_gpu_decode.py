@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200."""
+import gzip
+import hashlib
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import corpus
+import pngio
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+PNGSUITE = sorted(f for f in os.listdir(os.path.join(GOLDEN, "pngsuite")) if f.endswith(".png"))
+DIGESTS = json.load(open(os.path.join(GOLDEN, "pngsuite_rgba.json")))
+
+
+def job_of(png):
+    return dict(idat=png.idat, width=png.width, height=png.height, volume=png.volume,
+                depth=png.depth, interlaced=png.interlaced, fmt=png.fmt)
+
+
+def test_pngsuite_all_formats(pngb200, ctx, orc):
+    """all 161 PngSuite goldens through pngb200_decode_batch in ONE batch: storage == oracle
+    storage, and unpack(as: RGBA16) == the reference's .rgba golden"""
+    pngs = [pngio.parse(open(os.path.join(GOLDEN, "pngsuite", n), "rb").read()) for n in PNGSUITE]
+    got = pngb200.decode_batch(ctx, [job_of(p) for p in pngs])
+    for name, png, g in zip(PNGSUITE, pngs, got):
+        st, storage, res = orc.png_decode(png.idat, png.width, png.height, png.volume, png.depth, png.interlaced)
+        assert g.status == st == 0, name
+        assert g.pixels == storage, name
+        assert g.checksum == res.checksum and g.produced == res.produced, name
+        rgba = pngio.unpack_rgba16(png, g.pixels).astype("<u2").tobytes()
+        assert hashlib.sha256(rgba).hexdigest() == DIGESTS[name]["sha256"], name
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pngsuite_both_inflate_kernels(pngb200, ctx, orc, mode):
+    ctx.set_inflate_mode(mode)
+    try:
+        pngs = [pngio.parse(open(os.path.join(GOLDEN, "pngsuite", n), "rb").read()) for n in PNGSUITE]
+        got = pngb200.decode_batch(ctx, [job_of(p) for p in pngs])
+        for name, png, g in zip(PNGSUITE, pngs, got):
+            st, storage, _ = orc.png_decode(png.idat, png.width, png.height, png.volume, png.depth, png.interlaced)
+            assert g.status == st == 0 and g.pixels == storage, name
+    finally:
+        ctx.set_inflate_mode(0)
+
+
+SHAPES = [(1, 1), (3, 2), (4, 33), (17, 5), (33, 64), (64, 33), (100, 100), (257, 65), (640, 97)]
+
+
+@pytest.mark.parametrize("bpp,depth", [(1, 8), (2, 8), (3, 8), (4, 8), (6, 16), (8, 16), (2, 16)])
+def test_unfilter_random_filters(pngb200, ctx, orc, bpp, depth):
+    """every filter type on every row position / width residue, wavefront kernel vs oracle"""
+    rng = np.random.default_rng(bpp * 100 + depth)
+    jobs, want = [], []
+    for (w, h) in SHAPES:
+        pitch = w * bpp
+        rows = rng.integers(0, 256, size=(h, pitch + 1), dtype=np.uint8)
+        rows[:, 0] = rng.integers(0, 5, size=h)
+        if h > 3:
+            rows[3, 0] = 9  # invalid filter byte: passthrough quirk
+        filtered = rows.tobytes()
+        jobs.append(dict(filtered=filtered, width=w, height=h, volume=8 * bpp, depth=depth))
+        st, px = orc.png_unfilter(filtered, w, h, 8 * bpp, depth)
+        assert st == 0
+        want.append(px)
+    got = pngb200.unfilter_batch(ctx, jobs)
+    for (w, h), (st, px), ref in zip(SHAPES, got, want):
+        assert st == 0 and px == ref, (w, h, bpp)
+
+
+@pytest.mark.parametrize("ftype", [0, 1, 2, 3, 4])
+def test_unfilter_single_type_tall(pngb200, ctx, orc, ftype):
+    """one filter type for a whole tall image: exercises the band-to-band pipeline (many bands)"""
+    rng = np.random.default_rng(ftype)
+    w, h, bpp = 300, 700, 4
+    rows = rng.integers(0, 256, size=(h, w * bpp + 1), dtype=np.uint8)
+    rows[:, 0] = ftype
+    st, ref = orc.png_unfilter(rows.tobytes(), w, h, 32, 8)
+    (gst, px), = pngb200.unfilter_batch(ctx, [dict(filtered=rows.tobytes(), width=w, height=h, volume=32, depth=8)])
+    assert gst == st == 0 and px == ref
+
+
+def test_unfilter_interlaced_and_subbyte(pngb200, ctx, orc):
+    rng = np.random.default_rng(7)
+    jobs, want = [], []
+    for (w, h, vol, depth, il) in [(9, 9, 1, 1, True), (33, 17, 2, 2, False), (40, 40, 4, 4, True),
+                                   (31, 31, 32, 8, True), (5, 3, 64, 16, True), (12, 7, 24, 8, True),
+                                   (1, 1, 8, 8, True), (2, 3, 16, 16, True)]:
+        n = orc.filtered_size(w, h, vol, il)
+        filtered = bytearray(rng.integers(0, 256, size=n, dtype=np.uint8).tobytes())
+        # put valid filter bytes at row starts
+        st, _ = orc.png_unfilter(bytes(filtered), w, h, vol, depth, il)
+        jobs.append(dict(filtered=bytes(filtered), width=w, height=h, volume=vol, depth=depth, interlaced=il))
+        want.append(orc.png_unfilter(bytes(filtered), w, h, vol, depth, il))
+    got = pngb200.unfilter_batch(ctx, jobs)
+    for j, (st, px), (rst, ref) in zip(jobs, got, want):
+        assert st == rst and px == ref, j["width"]
+
+
+def _streams():
+    rng = np.random.default_rng(11)
+    text = (b"the quick brown fox jumps over the lazy dog. " * 400)
+    out = {
+        "empty": b"",
+        "one": b"x",
+        "text9": text,
+        "zeros": bytes(100000),
+        "noise": rng.integers(0, 256, size=70000, dtype=np.uint8).tobytes(),
+        "rle258": b"ab" * 40000,
+        "mixed": text[:5000] + rng.integers(0, 256, size=5000, dtype=np.uint8).tobytes() + bytes(9000) + text,
+    }
+    return out
+
+
+@pytest.mark.parametrize("level,strategy", [(0, 0), (1, 0), (6, 0), (9, 0), (6, zlib.Z_FIXED), (9, zlib.Z_HUFFMAN_ONLY), (9, zlib.Z_RLE)])
+def test_inflate_zlib_streams(pngb200, ctx, orc, level, strategy):
+    """stored / fixed / dynamic blocks, literals-only, long RLE matches"""
+    items = _streams()
+    comp = []
+    for k, v in items.items():
+        c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strategy)
+        comp.append(c.compress(v) + c.flush())
+    got = pngb200.inflate_batch(ctx, comp, pngb200.FORMAT_ZLIB, caps=[len(v) for v in items.values()])
+    for (k, v), c, (st, out, d) in zip(items.items(), comp, got):
+        ost, oout, ores = orc.inflate(c)
+        assert st == ost == 0, (k, st, d.err_a, d.err_b)
+        assert out == oout == v, k
+        assert d.checksum == ores.checksum == zlib.adler32(v), k
+        assert d.blocks == ores.blocks and d.consumed_bits == ores.consumed_bits, k
+
+
+def test_inflate_formats(pngb200, ctx, orc):
+    data = b"gzip and raw deflate " * 1000
+    raw = zlib.compressobj(9, zlib.DEFLATED, -15)
+    rawc = raw.compress(data) + raw.flush()
+    gz = gzip.compress(data, 9)
+    (st, out, d), = pngb200.inflate_batch(ctx, [rawc], pngb200.FORMAT_IOS, caps=[len(data)])
+    assert st == 0 and out == data and d.checksum == zlib.adler32(data)
+    (st, out, d), = pngb200.inflate_batch(ctx, [gz], pngb200.FORMAT_GZIP, caps=[len(data)])
+    assert st == 0 and out == data and d.checksum == zlib.crc32(data)
+    for name in ["empty.gz", "single-byte.gz", "GzipCompression.txt.gz", "GzipCompression.gz"]:
+        blob = open(os.path.join(GOLDEN, "gzip", name), "rb").read()
+        assert pngb200.gzip_extract(ctx, blob, cap=1 << 16) == gzip.decompress(blob)
+
+
+def test_inflate_errors_match_oracle(pngb200, ctx, orc):
+    payload = b"hello hello hello hello" * 10
+    good = zlib.compress(payload, 9)
+    bad_adler = bytearray(good); bad_adler[-1] ^= 1
+    cases = [good[:-5], good[:7], good[:2], b"", bytes(bad_adler), b"\x79\x9c" + good[2:], b"\x88\x1c" + good[2:],
+             b"\x78\x9d" + good[2:], b"\x78\xbb" + good[2:], b"\x78\x9c\x07", b"\x78\x9c\x01\x01\x00\x00\x00",
+             b"\x78\x9c\x05\xc0\x81\x00\x00\x00\x00\x00",  # dynamic block, bad code-length code
+             ]
+    rng = np.random.default_rng(5)
+    for i in range(40):  # random corruption of a dynamic stream
+        c = bytearray(zlib.compress(bytes(rng.integers(0, 64, size=3000, dtype=np.uint8)), 9))
+        for _ in range(3):
+            c[int(rng.integers(2, len(c)))] ^= 1 << int(rng.integers(0, 8))
+        cases.append(bytes(c))
+    got = pngb200.inflate_batch(ctx, cases, pngb200.FORMAT_ZLIB, caps=[1 << 16] * len(cases))
+    for c, (st, out, d) in zip(cases, got):
+        ost, oout, ores = orc.inflate(c, cap=1 << 16)
+        assert st == ost, (c[:8], st, ost)
+        if st == pngb200.ERR_STREAM_CHECKSUM:
+            assert (d.err_a, d.err_b) == (ores.a, ores.b)
+        if st >= 0:
+            assert out == oout
+    (st, out, d), = pngb200.inflate_batch(ctx, [good], pngb200.FORMAT_ZLIB, caps=[10])
+    assert st == pngb200.ERR_OUTPUT_CAPACITY
+
+
+def test_decode_synthetic_corpus(pngb200, ctx, orc):
+    """S0/S1/S2 RGBA8 + RGBA16 images, zlib level 6 with the reference's filter rule"""
+    jobs, want = [], []
+    for kind, w, h, sixteen in [("photo", 256, 192, False), ("graphic", 256, 192, False), ("noise", 128, 64, False),
+                                ("photo", 160, 120, True), ("photo", 1920, 64, False), ("graphic", 1000, 333, False)]:
+        img = corpus.make(kind, w, h, 0, sixteen)
+        bpp = 8 if sixteen else 4
+        filtered, comp = corpus.zlib_png_stream(img, bpp, 6)
+        assert filtered == orc.png_filter(img.tobytes(), w, h, 8 * bpp, 16 if sixteen else 8)
+        jobs.append(dict(idat=comp, width=w, height=h, volume=8 * bpp, depth=16 if sixteen else 8))
+        want.append(img.tobytes())
+    got = pngb200.decode_batch(ctx, jobs)
+    for g, ref, j in zip(got, want, jobs):
+        assert g.status == 0 and g.pixels == ref, (j["width"], j["height"])
+        assert g.checksum == orc.adler32(orc.png_filter(ref, j["width"], j["height"], j["volume"], j["depth"]))
+
+
+def test_decode_error_mapping(pngb200, ctx, orc):
+    """PNG.Decoder / PNG.Context error cases: truncated stream -> incompleteImageData...,
+    too many bytes -> extraneousImageData, short-but-complete stream -> ok"""
+    w, h = 16, 8
+    rng = np.random.default_rng(3)
+    rows = rng.integers(0, 256, size=(h, w * 4 + 1), dtype=np.uint8)
+    rows[:, 0] = rng.integers(0, 5, size=h)
+    f = rows.tobytes()
+    cases = [zlib.compress(f)[:-9], zlib.compress(f + b"\x00" * 3), zlib.compress(f[:-65]),
+             zlib.compress(f + bytes(1000))]
+    got = pngb200.decode_batch(ctx, [dict(idat=c, width=w, height=h, volume=32, depth=8) for c in cases])
+    for c, g in zip(cases, got):
+        st, storage, _ = orc.png_decode(c, w, h, 32, 8)
+        assert g.status == st, (g.status, st)
+    assert [g.status for g in got] == [pngb200.ERR_PNG_INCOMPLETE_DATASTREAM, pngb200.ERR_PNG_EXTRANEOUS_IMAGE_DATA,
+                                       pngb200.OK, pngb200.ERR_PNG_EXTRANEOUS_IMAGE_DATA]
+    # the rows that were available are decoded
+    st, storage, _ = orc.png_decode(cases[2], w, h, 32, 8)
+    assert got[2].pixels[: (h - 1) * w * 4] == storage[: (h - 1) * w * 4]
+
+
+def test_filter_batch_matches_oracle(pngb200, ctx, orc):
+    rng = np.random.default_rng(21)
+    jobs, want = [], []
+    for (w, h, vol, depth, il) in [(24, 16, 8, 8, False), (24, 16, 24, 8, False), (100, 37, 32, 8, False),
+                                   (33, 9, 64, 16, False), (256, 128, 32, 8, False), (9, 9, 1, 1, True),
+                                   (17, 5, 4, 4, False), (31, 33, 32, 8, True), (64, 64, 48, 16, False)]:
+        if depth >= 8:
+            img = corpus.make("photo", w, h, 1)[..., : max(1, vol // 8)] if vol <= 32 else corpus.make("photo", w, h, 1, True)[..., : vol // 8]
+            storage = np.ascontiguousarray(img).tobytes()
+        else:
+            storage = rng.integers(0, 1 << depth, size=w * h, dtype=np.uint8).tobytes()
+        jobs.append(dict(pixels=storage, width=w, height=h, volume=vol, depth=depth, interlaced=il))
+        want.append(orc.png_filter(storage, w, h, vol, depth, il))
+    got = pngb200.filter_batch(ctx, jobs)
+    for j, g, ref in zip(jobs, got, want):
+        assert g == ref, (j["width"], j["height"], j["volume"])
+
+
+def test_streaming_inflator(pngb200, ctx, orc):
+    """LZ77.Inflator push/pull semantics: slices of arbitrary size, pull(n) exact-or-None"""
+    rng = np.random.default_rng(2)
+    data = corpus.make("photo", 200, 150, 3).tobytes()
+    comp = zlib.compress(data, 6)
+    z = pngb200.Inflator(ctx, pngb200.FORMAT_ZLIB)
+    out, at = b"", 0
+    sizes = [1, 1, 3, 100, 4000, 1, 65536, 10 ** 9]
+    status = None
+    for s in sizes:
+        if at >= len(comp):
+            break
+        status = z.push(comp[at:at + s])
+        at += s
+        while True:
+            row = z.pull(801)
+            if row is None:
+                break
+            out += row
+    assert status == pngb200.OK
+    out += z.pull_all()
+    assert out == data
+    z.close()
+    # error surfaces as an exception with the Swift enum's payload
+    bad = bytearray(comp); bad[-2] ^= 0x55
+    z = pngb200.Inflator(ctx)
+    with pytest.raises(pngb200.PNGB200Error) as e:
+        z.push(bytes(bad))
+    assert e.value.status == pngb200.ERR_STREAM_CHECKSUM and e.value.payload[1] == zlib.adler32(data)
+    z.close()
