@@ -276,21 +276,17 @@ __device__ int read_trailer(BitReader& br, int format, StreamResult* r)
     return PNGB200_OK;
 }
 
-__global__ void __launch_bounds__(32) inflate_serial_kernel(const StreamJob* jobs, StreamResult* results, int count)
+// The whole serial decode of one stream by one warp, from (start_bit, start_out, phase).
+// `r` must have been zeroed (status 0) by the caller.
+__device__ void serial_inflate(SerialShared& sh, const StreamJob& job, StreamResult* r, uint64_t start_bit,
+                               uint64_t start_out, uint32_t phase, uint32_t blocks)
 {
-    __shared__ SerialShared sh;
-    int j = blockIdx.x;
-    if (j >= count) return;
-    const StreamJob job  = jobs[j];
-    StreamResult*   r    = results + j;
-    const unsigned  lane = lane_id();
-    BitReader       br;
-    br.init(job.src, job.src_len, job.start_bit);
-    uint64_t out    = job.start_out;
-    uint32_t blocks = 0;
-    int      st     = PNGB200_OK;
-    uint64_t resume_bit = job.start_bit, resume_out = job.start_out;
-    uint32_t phase = (uint32_t)job.phase;
+    const unsigned lane = lane_id();
+    BitReader      br;
+    br.init(job.src, job.src_len, start_bit);
+    uint64_t out = start_out;
+    int      st  = PNGB200_OK;
+    uint64_t resume_bit = start_bit, resume_out = start_out;
 
     if (phase == 0) {
         st = read_stream_header(br, job.format, r);
@@ -382,6 +378,16 @@ __global__ void __launch_bounds__(32) inflate_serial_kernel(const StreamJob* job
         r->resume_out    = resume_out;
         r->phase         = phase;
     }
+}
+
+__global__ void __launch_bounds__(32) inflate_serial_kernel(const StreamJob* jobs, StreamResult* results,
+                                                            const uint32_t* order, int count)
+{
+    __shared__ SerialShared sh;
+    if ((int)blockIdx.x >= count) return;
+    const int j = order ? (int)order[blockIdx.x] : (int)blockIdx.x;
+    const StreamJob job = jobs[j];
+    serial_inflate(sh, job, results + j, job.start_bit, job.start_out, (uint32_t)job.phase, 0);
 }
 
 }  // namespace pngb200

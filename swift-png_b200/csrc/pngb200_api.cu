@@ -14,6 +14,7 @@
 #include "checksum.cuh"
 #include "common.cuh"
 #include "filter.cuh"
+#include "inflate_parallel.cuh"
 #include "inflate_serial.cuh"
 #include "unfilter.cuh"
 
@@ -90,9 +91,10 @@ struct pngb200_ctx {
     bool         pending = false;
     int          pending_memspace = 0;
     // device workspaces (grow-only)
-    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_par;
+    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order;
     // pinned host tables
-    PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc;
+    PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order;
+    size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
     // geometry of the pending decode batch
     std::vector<uint64_t> expected;   // filtered bytes expected per image
     std::vector<size_t>   out_offset; // staging offsets (HOST memspace)
@@ -142,9 +144,35 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
     StreamJob*    d_jobs    = ctx->d_jobs.as<StreamJob>();
     StreamResult* d_results = ctx->d_results.as<StreamResult>();
     CU(cudaMemsetAsync(d_results, 0, sizeof(StreamResult) * count, ctx->stream));
-    inflate_serial_kernel<<<(unsigned)count, 32, 0, ctx->stream>>>(d_jobs, d_results, (int)count);
-    ctx->launches++;
-    CU(cudaGetLastError());
+    // big streams get a whole CTA each (block-parallel kernel); tiny ones a warp each
+    {
+        std::vector<uint32_t> par, ser;
+        for (size_t i = 0; i < count; ++i) {
+            bool big = h_jobs[i].src_len >= ctx->parallel_threshold;
+            if (ctx->inflate_mode == 1) big = false;
+            if (ctx->inflate_mode == 2) big = true;
+            (big ? par : ser).push_back((uint32_t)i);
+        }
+        CU(ctx->h_order.reserve(sizeof(uint32_t) * count));
+        CU(ctx->d_order.reserve(sizeof(uint32_t) * count));
+        uint32_t* ho = ctx->h_order.as<uint32_t>();
+        std::copy(par.begin(), par.end(), ho);
+        std::copy(ser.begin(), ser.end(), ho + par.size());
+        CU(cudaMemcpyAsync(ctx->d_order.p, ho, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+        const uint32_t* d_order = ctx->d_order.as<uint32_t>();
+        if (!par.empty()) {
+            int rc = launch_inflate_parallel(ctx->stream, d_jobs, d_results, d_order, (int)par.size(), &ctx->launches);
+            if (rc != 0)
+                return set_error(ctx, PNGB200_ERR_CUDA, "inflate_parallel_kernel launch failed: %s",
+                                 cudaGetErrorString((cudaError_t)rc));
+        }
+        if (!ser.empty()) {
+            inflate_serial_kernel<<<(unsigned)ser.size(), 32, 0, ctx->stream>>>(d_jobs, d_results, d_order + par.size(),
+                                                                                 (int)ser.size());
+            ctx->launches++;
+        }
+        CU(cudaGetLastError());
+    }
     // checksum: chunk layout from dst_cap (an upper bound of `produced`)
     CU(ctx->h_misc.reserve(sizeof(uint32_t) * (count + 1)));
     uint32_t* base = ctx->h_misc.as<uint32_t>();
@@ -333,6 +361,11 @@ pngb200_ctx* pngb200_ctx_create(int device)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
+    if (configure_inflate_parallel() != 0) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(ParShared));
+        delete ctx;
+        return nullptr;
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error(nullptr, PNGB200_ERR_CUDA, "cudaStreamCreate failed");
         delete ctx;
@@ -347,9 +380,9 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->d_jobs, &ctx->d_results, &ctx->d_imgjobs, &ctx->d_genjobs, &ctx->d_misc,
-                      &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_par})
+                      &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_order})
         b->release();
-    for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc})
+    for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order})
         b->release();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -757,7 +790,7 @@ int pngb200_inflator_push(pngb200_inflator* z, const uint8_t* data, size_t n)
         job->phase = (int32_t)z->phase;
         CU(cudaMemcpyAsync(z->d_job.p, job, sizeof(StreamJob), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(z->d_res.p, 0, sizeof(StreamResult), ctx->stream));
-        inflate_serial_kernel<<<1, 32, 0, ctx->stream>>>(z->d_job.as<StreamJob>(), z->d_res.as<StreamResult>(), 1);
+        inflate_serial_kernel<<<1, 32, 0, ctx->stream>>>(z->d_job.as<StreamJob>(), z->d_res.as<StreamResult>(), nullptr, 1);
         ctx->launches++;
         // checksum over everything produced so far (cheap relative to the inflate itself)
         uint32_t base[2] = {0, (uint32_t)((z->d_out.cap + CK_CHUNK - 1) / CK_CHUNK)};
