@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- MPixels/s of the PNG decode hot path (inflate + unfilter) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+
+A "step" decodes one batch of synthetic PNG image streams resident in HBM (value) or in pinned
+host memory (e2e).  Workload (default): B x 7680x4320 RGBA8 "photo" images per GPU (SURVEY.md
+section 8d corpus S0), compressed with zlib level 6 after the reference's filter rule.  Images
+are independent, so ranks share nothing on the data path (weak scaling: B images per GPU).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import zlib
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (width, height, sixteen, default batch per GPU, default unique images)
+    "8k-rgba8": (7680, 4320, False, 148, 2),
+    "1080p-rgba8": (1920, 1080, False, 1024, 16),
+    "8k-rgba16": (7680, 4320, True, 8, 2),
+    "small": (512, 512, False, 64, 4),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="8k-rgba8", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (0 = workload default)")
+    ap.add_argument("--unique", type=int, default=0, help="distinct images (0 = workload default)")
+    ap.add_argument("--kind", default="photo", choices=["photo", "graphic", "noise"])
+    ap.add_argument("--level", type=int, default=6, help="zlib level of the input streams")
+    ap.add_argument("--inflate-mode", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-images", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ corpus
+def make_corpus(args, pkg, ctx):
+    """U unique images -> (pixels bytes, filtered adler, zlib stream).  Filtering uses OUR
+    filter-select kernel when a context exists (the oracle is only the cpu_baseline / checker)."""
+    import corpus
+    w, h, sixteen, _, _ = WORKLOADS[args.workload]
+    bpp = 8 if sixteen else 4
+    out = []
+    for i in range(args.unique):
+        img = corpus.make(args.kind, w, h, i, sixteen) if args.kind == "photo" else corpus.make(args.kind, w, h, i)
+        storage = np.ascontiguousarray(img).tobytes()
+        if ctx is not None:
+            (filtered,) = pkg.filter_batch(ctx, [dict(pixels=storage, width=w, height=h, volume=8 * bpp,
+                                                      depth=16 if sixteen else 8)])
+        else:
+            from oracle import oracle
+            filtered = oracle.png_filter(storage, w, h, 8 * bpp, 16 if sixteen else 8)
+        comp = zlib.compress(filtered, args.level)
+        out.append(dict(pixels=storage, adler=zlib.adler32(filtered), idat=comp, filtered_len=len(filtered)))
+    return out
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([x.strip() for x in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------ cpu (oracle) leg
+def cpu_decode_rate(corpus_items, w, h, bpp, depth, nimages: int, threads: int):
+    """MPixels/s of the CPU restatement of the reference on `nimages` decodes over `threads`
+    host threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle
+    oracle.lib()
+    jobs = [corpus_items[i % len(corpus_items)] for i in range(nimages)]
+
+    def one(item):
+        st, storage, res = oracle.png_decode(item["idat"], w, h, 8 * bpp, depth)
+        assert st == 0
+        return len(storage)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, jobs))
+    dt = time.perf_counter() - t0
+    return nimages * w * h / dt / 1e6, dt
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    args = parse_args()
+    w, h, sixteen, dbatch, dunique = WORKLOADS[args.workload]
+    args.batch = args.batch or dbatch
+    args.unique = min(args.unique or dunique, args.batch)
+    bpp, depth = (8, 16) if sixteen else (4, 8)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"{args.batch}x {w}x{h} RGBA{depth} per GPU ({args.kind}, zlib level {args.level}, "
+                          f"reference filter rule; {args.unique} distinct images)",
+              "images_per_gpu": args.batch, "l2": "inputs larger than L2 (no flush needed)"}
+
+    # ---------------- reference arm: the CPU restatement on the host cores ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        items = make_corpus(args, None, None)
+        threads = os.cpu_count() or 1
+        per_step = args.cpu_images or max(threads, 1)
+        if w * h > 4_000_000:
+            per_step = args.cpu_images or max(min(threads, 16), 1)
+        for _ in range(max(args.warmup, 0) and 1):
+            cpu_decode_rate(items, w, h, bpp, depth, min(per_step, threads), threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_decode_rate(items, w, h, bpp, depth, per_step, threads)
+        dt = time.perf_counter() - t0
+        v = args.steps * per_step * w * h / dt / 1e6
+        line = {"impl": "reference", "metric": "MPixels/s decode (inflate+unfilter)", "value": v, "unit": "MPixels/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": v, "unit": "MPixels/s", "cores": threads, "kind": "port",
+                                 "sample": f"{per_step} images per step, {threads} host threads, C restatement "
+                                           "of the Swift reference (no Swift toolchain in the image)"},
+                "e2e": {"value": v, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("swift-png_b200")
+    ctx = pkg.Context(local_rank)
+    ctx.set_inflate_mode(args.inflate_mode)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    items = make_corpus(args, pkg, ctx)
+    B = args.batch
+    npix = w * h
+    storage_bytes = npix * bpp
+
+    # device-resident inputs (unique streams, referenced by many jobs) and outputs
+    d_idat = [torch.frombuffer(bytearray(it["idat"]), dtype=torch.uint8).cuda() for it in items]
+    d_pixels = torch.empty((B, storage_bytes), dtype=torch.uint8, device="cuda")
+    descs = (pkg.ImageDesc * B)()
+    for i in range(B):
+        u = i % len(items)
+        descs[i].idat = d_idat[u].data_ptr()
+        descs[i].idat_len = d_idat[u].numel()
+        descs[i].pixels = d_pixels[i].data_ptr()
+        descs[i].pixels_cap = storage_bytes
+        descs[i].width, descs[i].height = w, h
+        descs[i].volume, descs[i].depth = 8 * bpp, depth
+        descs[i].interlaced, descs[i].format = 0, 0
+    L = ctx._lib
+
+    def step_device():
+        ctx.check(L.pngb200_decode_batch_enqueue(ctx.handle, descs, B, pkg.MEM_DEVICE))
+        ctx.check(L.pngb200_decode_batch_finish(ctx.handle, descs, B))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    # bit-exactness in the same run: round trip == original pixels, Adler-32 == zlib's
+    torch.cuda.synchronize()
+    for u, it in enumerate(items):
+        ref = torch.frombuffer(bytearray(it["pixels"]), dtype=torch.uint8).cuda()
+        for i in range(u, B, len(items)):
+            assert descs[i].status == 0, (i, descs[i].status)
+            assert descs[i].checksum == it["adler"], i
+            assert torch.equal(d_pixels[i], ref), f"pixel mismatch in image {i}"
+        del ref
+    launches0 = ctx.launches
+    stage = np.zeros(3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+            stage += np.array(ctx.stage_ms())
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * npix * args.steps / (ms_max / 1e3) / 1e6
+    stage /= args.steps
+
+    # ---------------- e2e: same call, HOST (pinned) buffers, copies inside the timed region ----------------
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        per_image = storage_bytes + max(len(it["idat"]) for it in items)
+        avail = psutil.virtual_memory().available
+        EB = B
+        while EB > 8 and EB * per_image * 2.5 * max(world, 1) > avail:
+            EB //= 2  # pinned host staging for the whole batch must fit comfortably in host RAM
+        full_B, B = B, EB
+        comp_total = sum(len(items[i % len(items)]["idat"]) for i in range(B))
+        h_in = torch.empty(comp_total, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty((B, storage_bytes), dtype=torch.uint8).pin_memory()
+        hdescs = (pkg.ImageDesc * B)()
+        at = 0
+        for i in range(B):
+            it = items[i % len(items)]
+            n = len(it["idat"])
+            h_in[at:at + n] = torch.frombuffer(bytearray(it["idat"]), dtype=torch.uint8)
+            hdescs[i].idat = h_in.data_ptr() + at
+            hdescs[i].idat_len = n
+            hdescs[i].pixels = h_out[i].data_ptr()
+            hdescs[i].pixels_cap = storage_bytes
+            hdescs[i].width, hdescs[i].height = w, h
+            hdescs[i].volume, hdescs[i].depth = 8 * bpp, depth
+            at += n
+        del d_pixels
+        torch.cuda.empty_cache()
+
+        def step_host():
+            ctx.check(L.pngb200_decode_batch(ctx.handle, hdescs, B, pkg.MEM_HOST))
+
+        for _ in range(2):
+            step_host()
+        assert bytes(h_out[B - 1].numpy().tobytes()) == items[(B - 1) % len(items)]["pixels"]
+        barrier()
+        t0 = time.perf_counter()
+        esteps = max(1, min(args.steps, 3))
+        for _ in range(esteps):
+            step_host()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * npix * esteps / float(dt.item()) / 1e6, "unit": "MPixels/s",
+               "h2d_bytes_per_step": comp_total, "d2h_bytes_per_step": B * storage_bytes, "steps": esteps,
+               "images_per_gpu": B,
+               "note": "pngb200_decode_batch with pinned HOST buffers: H2D of the IDAT streams and D2H of the "
+                       "decoded pixels are inside the timed region (host wall clock, max over ranks)"}
+        B = full_B
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (inflate), measured live ----------------
+    peak, peak_src = peaks()
+    comp_step = sum(len(items[i % len(items)]["idat"]) for i in range(B))
+    alg_bytes = comp_step + B * storage_bytes  # C + P per image x images per launch
+    dominant = int(np.argmax(stage))
+    names = ["inflate_parallel_kernel", "checksum kernels", "unfilter_wave_kernel"]
+    achieved = alg_bytes / (stage[0] / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    roofline = {"bound": "hbm", "kernel": names[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "stage_ms": {"inflate": stage[0], "checksum": stage[1], "unfilter": stage[2]},
+                "dominant_stage": names[dominant],
+                "whole_step_frac": alg_bytes / (ms_max / args.steps / 1e3) / 1e9 / peak}
+
+    cpu = None
+    if not args.no_cpu:
+        threads = min(os.cpu_count() or 1, 16)
+        n_cpu = args.cpu_images or (threads if npix > 4_000_000 else 4 * threads)
+        v, dt = cpu_decode_rate(items, w, h, bpp, depth, n_cpu, threads)
+        cpu = {"value": v, "unit": "MPixels/s", "cores": threads, "kind": "port",
+               "sample": f"{n_cpu} images of the same workload over {threads} host threads in {dt:.1f}s; "
+                         "C restatement of the Swift reference (oracle/), no Swift toolchain in the image"}
+
+    line = {"metric": "MPixels/s decode (inflate+unfilter)", "value": value, "unit": "MPixels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": config, "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "bit_exact": True}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,9 @@ uint64_t     pngb200_ctx_launch_count(const pngb200_ctx* ctx);
 /* tuning knob: 0 = automatic, 1 = force the one-warp-per-stream inflate kernel,
  * 2 = force the block-parallel inflate kernel */
 void         pngb200_ctx_set_inflate_mode(pngb200_ctx* ctx, int mode);
+/* device time (CUDA events on the context's stream) of the last completed decode batch's stages:
+ * ms[0] inflate kernels, ms[1] checksum kernels, ms[2] unfilter kernels */
+int          pngb200_ctx_stage_ms(pngb200_ctx* ctx, float ms[3]);
 
 /* ---- batched one-shot entry points (the throughput path) ---- */
 

@@ -128,6 +128,8 @@ def lib():
     L.pngb200_ctx_launch_count.restype = C.c_uint64
     L.pngb200_ctx_set_inflate_mode.argtypes = [C.c_void_p, C.c_int]
     L.pngb200_ctx_set_inflate_mode.restype = None
+    L.pngb200_ctx_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.pngb200_ctx_stage_ms.restype = C.c_int
     L.pngb200_inflate_batch.argtypes = [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_int]
     L.pngb200_inflate_batch.restype = C.c_int
     for name in ("pngb200_decode_batch", "pngb200_decode_batch_enqueue", "pngb200_unfilter_batch"):
@@ -201,6 +203,12 @@ class Context:
     @property
     def launches(self) -> int:
         return self._lib.pngb200_ctx_launch_count(self.handle)
+
+    def stage_ms(self):
+        """(inflate, checksum, unfilter) device milliseconds of the last finished decode batch"""
+        ms = (C.c_float * 3)()
+        self.check(self._lib.pngb200_ctx_stage_ms(self.handle, ms))
+        return tuple(ms)
 
     def set_inflate_mode(self, mode: int):
         self._lib.pngb200_ctx_set_inflate_mode(self.handle, mode)

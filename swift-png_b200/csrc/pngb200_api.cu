@@ -95,6 +95,7 @@ struct pngb200_ctx {
     // pinned host tables
     PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order;
     size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // decode stage boundaries
     // geometry of the pending decode batch
     std::vector<uint64_t> expected;   // filtered bytes expected per image
     std::vector<size_t>   out_offset; // staging offsets (HOST memspace)
@@ -144,6 +145,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
     StreamJob*    d_jobs    = ctx->d_jobs.as<StreamJob>();
     StreamResult* d_results = ctx->d_results.as<StreamResult>();
     CU(cudaMemsetAsync(d_results, 0, sizeof(StreamResult) * count, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     // big streams get a whole CTA each (block-parallel kernel); tiny ones a warp each
     {
         std::vector<uint32_t> par, ser;
@@ -173,6 +175,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
         }
         CU(cudaGetLastError());
     }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     // checksum: chunk layout from dst_cap (an upper bound of `produced`)
     CU(ctx->h_misc.reserve(sizeof(uint32_t) * (count + 1)));
     uint32_t* base = ctx->h_misc.as<uint32_t>();
@@ -201,6 +204,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
     checksum_fold_kernel<<<(unsigned)count, 32, 0, ctx->stream>>>(cp);
     ctx->launches++;
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     return PNGB200_OK;
 }
 
@@ -371,6 +375,7 @@ pngb200_ctx* pngb200_ctx_create(int device)
         delete ctx;
         return nullptr;
     }
+    for (cudaEvent_t& e : ctx->ev) cudaEventCreate(&e);
     return ctx;
 }
 
@@ -384,6 +389,7 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
         b->release();
     for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order})
         b->release();
+    for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -393,6 +399,18 @@ void*       pngb200_ctx_stream(pngb200_ctx* ctx) { return ctx ? (void*)ctx->stre
 int         pngb200_ctx_device(const pngb200_ctx* ctx) { return ctx ? ctx->device : -1; }
 uint64_t    pngb200_ctx_launch_count(const pngb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void        pngb200_ctx_set_inflate_mode(pngb200_ctx* ctx, int mode) { if (ctx) ctx->inflate_mode = mode; }
+
+int pngb200_ctx_stage_ms(pngb200_ctx* ctx, float ms[3])
+{
+    if (!ctx || !ms) return PNGB200_ERR_BAD_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    for (int i = 0; i < 3; ++i)
+        if (cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(ctx, PNGB200_ERR_CUDA, "stage events not recorded yet");
+        }
+    return PNGB200_OK;
+}
 
 // ---------------- standalone inflate ----------------
 int pngb200_inflate_batch(pngb200_ctx* ctx, pngb200_stream_desc* s, size_t count, int memspace)
@@ -532,6 +550,7 @@ int pngb200_decode_batch_enqueue(pngb200_ctx* ctx, pngb200_image_desc* im, size_
     }
     rc = run_unfilter(ctx, items);
     if (rc != PNGB200_OK) return rc;
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     CU(cudaMemcpyAsync(ctx->h_results.p, ctx->d_results.p, sizeof(StreamResult) * count,
                        cudaMemcpyDeviceToHost, ctx->stream));
     if (host)
