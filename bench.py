@@ -249,6 +249,7 @@ def main():
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launches - launches0
+    stats = ctx.inflate_stats(B)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -343,7 +344,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config, "clocks": clocks.summary(), "gpu_launches": int(launches),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "bit_exact": True}
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "bit_exact": True,
+            "inflate_stats_per_step": stats}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -91,6 +91,10 @@ void         pngb200_ctx_set_inflate_mode(pngb200_ctx* ctx, int mode);
 /* device time (CUDA events on the context's stream) of the last completed decode batch's stages:
  * ms[0] inflate kernels, ms[1] checksum kernels, ms[2] unfilter kernels */
 int          pngb200_ctx_stage_ms(pngb200_ctx* ctx, float ms[3]);
+/* device-side counters of the last finished batch of `count` streams/images, summed:
+ * out[0] waves, out[1] sync rounds, out[2] copy-resolve rounds, out[3] streams that fell back to
+ * the serial decoder (the analogue of the reference's -DDUMP_LZ77_BLOCKS statistics) */
+int          pngb200_ctx_inflate_stats(pngb200_ctx* ctx, size_t count, uint64_t out[4]);
 
 /* ---- batched one-shot entry points (the throughput path) ---- */
 

@@ -130,6 +130,8 @@ def lib():
     L.pngb200_ctx_set_inflate_mode.restype = None
     L.pngb200_ctx_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.pngb200_ctx_stage_ms.restype = C.c_int
+    L.pngb200_ctx_inflate_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    L.pngb200_ctx_inflate_stats.restype = C.c_int
     L.pngb200_inflate_batch.argtypes = [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_int]
     L.pngb200_inflate_batch.restype = C.c_int
     for name in ("pngb200_decode_batch", "pngb200_decode_batch_enqueue", "pngb200_unfilter_batch"):
@@ -209,6 +211,12 @@ class Context:
         ms = (C.c_float * 3)()
         self.check(self._lib.pngb200_ctx_stage_ms(self.handle, ms))
         return tuple(ms)
+
+    def inflate_stats(self, count: int):
+        """dict of device-side counters summed over the last batch of `count` items"""
+        out = (C.c_uint64 * 4)()
+        self.check(self._lib.pngb200_ctx_inflate_stats(self.handle, count, out))
+        return dict(waves=out[0], sync_rounds=out[1], resolve_rounds=out[2], fallbacks=out[3])
 
     def set_inflate_mode(self, mode: int):
         self._lib.pngb200_ctx_set_inflate_mode(self.handle, mode)

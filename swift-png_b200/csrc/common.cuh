@@ -32,6 +32,8 @@ struct StreamResult {
     uint64_t resume_out;      // output size at resume_bit
     uint32_t trailer_seen;    // 1 when the final block and trailer were parsed
     uint32_t phase;           // phase to resume in at resume_bit (see StreamJob.phase)
+    // device-side counters (the reference's -DDUMP_LZ77_BLOCKS style statistics)
+    uint32_t stat_waves, stat_sync_rounds, stat_resolve_rounds, stat_fallback;
 };
 
 // One image for the unfilter stage.

@@ -91,7 +91,7 @@ struct pngb200_ctx {
     bool         pending = false;
     int          pending_memspace = 0;
     // device workspaces (grow-only)
-    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order;
+    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order, d_scratch;
     // pinned host tables
     PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order;
     size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
@@ -155,6 +155,9 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             if (ctx->inflate_mode == 2) big = true;
             (big ? par : ser).push_back((uint32_t)i);
         }
+        // longest first: the persistent CTAs pull streams from a ticket, so this is LPT scheduling
+        std::stable_sort(par.begin(), par.end(),
+                         [&](uint32_t a, uint32_t b) { return h_jobs[a].src_len > h_jobs[b].src_len; });
         CU(ctx->h_order.reserve(sizeof(uint32_t) * count));
         CU(ctx->d_order.reserve(sizeof(uint32_t) * count));
         uint32_t* ho = ctx->h_order.as<uint32_t>();
@@ -163,10 +166,26 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
         CU(cudaMemcpyAsync(ctx->d_order.p, ho, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
         const uint32_t* d_order = ctx->d_order.as<uint32_t>();
         if (!par.empty()) {
-            int rc = launch_inflate_parallel(ctx->stream, d_jobs, d_results, d_order, (int)par.size(), &ctx->launches);
-            if (rc != 0)
-                return set_error(ctx, PNGB200_ERR_CUDA, "inflate_parallel_kernel launch failed: %s",
-                                 cudaGetErrorString((cudaError_t)rc));
+            uint64_t max_cap = 0;
+            for (uint32_t i : par) max_cap = std::max<uint64_t>(max_cap, h_jobs[i].dst_cap);
+            ParParams pp;
+            pp.bitmap_words = par_bitmap_words(max_cap);
+            pp.scratch_stride = par_scratch_stride(pp.bitmap_words);
+            unsigned grid = (unsigned)std::min<size_t>(par.size(), (size_t)ctx->sm_count);
+            size_t need = (size_t)pp.scratch_stride * grid + 256;
+            if (need > ctx->d_scratch.cap) {  // fresh scratch must start zeroed (the kernel keeps it clean)
+                CU(ctx->d_scratch.reserve(need));
+                CU(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, ctx->stream));
+            }
+            pp.ticket = (uint32_t*)((char*)ctx->d_scratch.p + (size_t)pp.scratch_stride * grid);
+            CU(cudaMemsetAsync(pp.ticket, 0, sizeof(uint32_t), ctx->stream));
+            pp.jobs = d_jobs;
+            pp.results = d_results;
+            pp.order = d_order;
+            pp.scratch = ctx->d_scratch.as<uint8_t>();
+            pp.count = (int)par.size();
+            inflate_parallel_kernel<<<grid, PAR_THREADS, sizeof(ParShared), ctx->stream>>>(pp);
+            ctx->launches++;
         }
         if (!ser.empty()) {
             inflate_serial_kernel<<<(unsigned)ser.size(), 32, 0, ctx->stream>>>(d_jobs, d_results, d_order + par.size(),
@@ -385,7 +404,7 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->d_jobs, &ctx->d_results, &ctx->d_imgjobs, &ctx->d_genjobs, &ctx->d_misc,
-                      &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_order})
+                      &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_order, &ctx->d_scratch})
         b->release();
     for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order})
         b->release();
@@ -399,6 +418,20 @@ void*       pngb200_ctx_stream(pngb200_ctx* ctx) { return ctx ? (void*)ctx->stre
 int         pngb200_ctx_device(const pngb200_ctx* ctx) { return ctx ? ctx->device : -1; }
 uint64_t    pngb200_ctx_launch_count(const pngb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void        pngb200_ctx_set_inflate_mode(pngb200_ctx* ctx, int mode) { if (ctx) ctx->inflate_mode = mode; }
+
+int pngb200_ctx_inflate_stats(pngb200_ctx* ctx, size_t count, uint64_t out[4])
+{
+    if (!ctx || !out || ctx->h_results.cap < sizeof(StreamResult) * count) return PNGB200_ERR_BAD_ARGUMENT;
+    const StreamResult* r = ctx->h_results.as<StreamResult>();
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (size_t i = 0; i < count; ++i) {
+        out[0] += r[i].stat_waves;
+        out[1] += r[i].stat_sync_rounds;
+        out[2] += r[i].stat_resolve_rounds;
+        out[3] += r[i].stat_fallback;
+    }
+    return PNGB200_OK;
+}
 
 int pngb200_ctx_stage_ms(pngb200_ctx* ctx, float ms[3])
 {
