@@ -49,14 +49,26 @@ constexpr uint64_t PAR_MAX_WAVE_OUT = (uint64_t)PAR_LIST_CAP * 258;
 
 enum : uint32_t { PF_EOB = 1, PF_BAD = 2 };
 
+struct ParHeader {  // block header as parsed by warp 0, broadcast to the CTA
+    int32_t  status, type, final, nlit, ndist;
+    uint32_t stored;
+    uint64_t pos;     // reader position after the header
+};
+
 struct ParShared {
     SerialShared ser;
     uint32_t     words[PAR_SMEM_WORDS];
-    uint32_t     exit_[PAR_THREADS];
+    uint32_t     start_[PAR_THREADS];   // per subsequence: decode start (wave-relative bit)
+    uint32_t     exit_[PAR_THREADS];    //                  first symbol boundary past its end
+    uint32_t     nout_[PAR_THREADS];    //                  output bytes
+    uint8_t      flag_[PAR_THREADS];    //                  PF_EOB / PF_BAD
+    uint16_t     list_[PAR_THREADS];    // compacted ids of subsequences that must be re-decoded
     uint32_t     bitmap[PAR_BITMAP_WORDS];
     uint32_t     warp_sums[32];
     uint32_t     npend[2];
-    uint32_t     first_need, first_stop, anomaly, ticket;
+    uint32_t     first_need[2], first_stop[2], nlist[2];
+    uint32_t     anomaly, ticket;
+    ParHeader    hdr;
 };
 
 struct ParParams {
@@ -86,13 +98,15 @@ struct SmemBits {
         cnt = 0;
         pos = start;
         refill();
+        refill();
         int skip = (int)(start & 31);
         buf >>= skip;
         cnt -= skip;
     }
+    // one word is always enough: a token takes <= 20 bits before the next refill and <= 28 after
     __device__ __forceinline__ void refill()
     {
-        while (cnt <= 32) {
+        if (cnt <= 32) {
             buf |= (uint64_t)w[wi + (wi >> 3)] << cnt;
             cnt += 32;
             ++wi;
@@ -182,8 +196,13 @@ __device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t a, ui
 __device__ __forceinline__ void lz_copy(uint8_t* to, uint32_t run, uint32_t dist)
 {
     const uint8_t* from = to - dist;
-    if (dist >= run) {
-        for (uint32_t k = 0; k < run; ++k) to[k] = from[k];
+    if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
+        uint32_t k = 0;
+        for (; k + 4 <= run; k += 4) {
+            uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
+            to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3;
+        }
+        for (; k < run; ++k) to[k] = from[k];
     } else {
         uint32_t q = 0;
         for (uint32_t k = 0; k < run; ++k) {
@@ -209,8 +228,9 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
         __syncthreads();
         if (t == 0) {
             sh.ticket = atomicAdd(P.ticket, 1u);
-            sh.first_need = PAR_THREADS;
-            sh.first_stop = PAR_THREADS;
+            sh.first_need[0] = sh.first_need[1] = PAR_THREADS;
+            sh.first_stop[0] = sh.first_stop[1] = PAR_THREADS;
+            sh.nlist[0] = sh.nlist[1] = 0;
             sh.anomaly = 0;
         }
         __syncthreads();
@@ -239,10 +259,25 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
         if (st == PNGB200_OK && phase == 2) st = read_trailer(br, job.format, r);
 
         while (st == PNGB200_OK && phase == 1) {
-            int      type, final;
-            uint32_t stored = 0;
-            st = read_block_header(br, &sh.ser, r, (int)t, PAR_THREADS, &type, &final, &stored);
+            // warp 0 walks the header bits alone; the CTA then builds the tables together
+            __syncthreads();
+            if (warp == 0) {
+                int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
+                uint32_t stored0 = 0;
+                int st0 = parse_block_header(br, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
+                if (lane == 0) sh.hdr = ParHeader{st0, type0, final0, nlit0, ndist0, stored0, br.pos};
+            }
+            __syncthreads();
+            const ParHeader hdr = sh.hdr;
+            st = hdr.status;
             if (st != PNGB200_OK) break;
+            const int      type = hdr.type, final = hdr.final;
+            const uint32_t stored = hdr.stored;
+            if (warp != 0) br.seek(hdr.pos);
+            if (type != 0) {
+                st = build_block_tables(&sh.ser, r, hdr.nlit, hdr.ndist, (int)t, PAR_THREADS);
+                if (st != PNGB200_OK) break;
+            }
             if (type == 0) {
                 if (!br.have(8 * (uint64_t)stored)) { st = PNGB200_NEED_MORE_INPUT; break; }
                 if (out + stored > job.dst_cap) { st = fail(r, PNGB200_ERR_OUTPUT_CAPACITY); break; }
@@ -261,36 +296,68 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
                     __syncthreads();
                     for (uint32_t k = t; k < PAR_WAVE_WORDS; k += PAR_THREADS)
                         sh.words[k + (k >> 3)] = br.load_word(wbase + k);
-                    if (t == 0) sh.npend[0] = 0;
+                    if (t == 0) {
+                        sh.npend[0] = 0;
+                        sh.first_need[0] = sh.first_need[1] = PAR_THREADS;
+                        sh.first_stop[0] = sh.first_stop[1] = PAR_THREADS;
+                        sh.nlist[0] = sh.nlist[1] = 0;
+                    }
                     __syncthreads();
                     const uint32_t rel0  = (uint32_t)(wstart - (wbase << 5));  // < 256
                     const uint32_t limit = (t + 1) * PAR_SUB_BITS;
-                    uint32_t my_start = t == 0 ? rel0 : t * PAR_SUB_BITS;
-                    uint32_t ex, n, fl;
-                    par_decode_count(sh, my_start, limit, ex, n, fl);
-                    // ---- sync rounds ----
+                    {
+                        uint32_t s0 = t == 0 ? rel0 : t * PAR_SUB_BITS, ex0, n0, fl0;
+                        par_decode_count(sh, s0, limit, ex0, n0, fl0);
+                        sh.start_[t] = s0;
+                        sh.exit_[t]  = ex0;
+                        sh.nout_[t]  = n0;
+                        sh.flag_[t]  = (uint8_t)fl0;
+                    }
+                    // ---- sync rounds: only subsequences whose start moved are re-decoded, compacted
+                    //      onto the lowest threads so that a round costs what it re-decodes ----
                     uint32_t nvalid = PAR_THREADS;
                     bool     stop_found = false;
-                    for (;;) {
+                    for (uint32_t round = 0;; ++round) {
+                        const uint32_t p = round & 1;
                         ++sync_rounds;
-                        sh.exit_[t] = ex;
                         __syncthreads();
-                        const bool need = t > 0 && sh.exit_[t - 1] != my_start;
-                        if (need) atomicMin(&sh.first_need, t);
+                        if (t == 0) {  // the other parity's counters are idle during this round
+                            sh.first_need[p ^ 1] = PAR_THREADS;
+                            sh.first_stop[p ^ 1] = PAR_THREADS;
+                            sh.nlist[p ^ 1] = 0;
+                        }
+                        const uint32_t prev_exit = t > 0 ? sh.exit_[t - 1] : 0;
+                        const bool need = t > 0 && prev_exit != sh.start_[t];
+                        if (need) atomicMin(&sh.first_need[p], t);
                         __syncthreads();
-                        const uint32_t fn = sh.first_need;
-                        if (t < fn && fl != 0) atomicMin(&sh.first_stop, t);
+                        const uint32_t fn = sh.first_need[p];
+                        if (t < fn && sh.flag_[t] != 0) atomicMin(&sh.first_stop[p], t);
                         __syncthreads();
-                        const uint32_t fs = sh.first_stop;
-                        __syncthreads();
-                        if (t == 0) { sh.first_need = PAR_THREADS; sh.first_stop = PAR_THREADS; }
+                        const uint32_t fs = sh.first_stop[p];
                         if (fs < PAR_THREADS) { nvalid = fs + 1; stop_found = true; break; }
                         if (fn == PAR_THREADS) break;
+                        const unsigned ballot = __ballot_sync(0xffffffffu, need);
                         if (need) {
-                            my_start = sh.exit_[t - 1];
-                            par_decode_count(sh, my_start, limit, ex, n, fl);
+                            uint32_t base = 0;
+                            const int leader = __ffs(ballot) - 1;
+                            if ((int)lane == leader) base = atomicAdd(&sh.nlist[p], (uint32_t)__popc(ballot));
+                            base = __shfl_sync(ballot, base, leader);
+                            sh.list_[base + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)t;
+                            sh.start_[t] = prev_exit;
+                        }
+                        __syncthreads();
+                        const uint32_t cnt = sh.nlist[p];
+                        if (t < cnt) {
+                            const uint32_t u = sh.list_[t];
+                            uint32_t ex0, n0, fl0;
+                            par_decode_count(sh, sh.start_[u], (u + 1) * PAR_SUB_BITS, ex0, n0, fl0);
+                            sh.exit_[u] = ex0;
+                            sh.nout_[u] = n0;
+                            sh.flag_[u] = (uint8_t)fl0;
                         }
                     }
+                    __syncthreads();
+                    const uint32_t my_start = sh.start_[t], ex = sh.exit_[t], n = sh.nout_[t], fl = sh.flag_[t];
                     // ---- anomalies on the verified chain -> serial decoder ----
                     if (t == nvalid - 1 && ((fl & PF_BAD) || (wbase << 5) + ex > br.total_bits)) sh.anomaly = 1;
                     // ---- scan of output counts ----

@@ -149,19 +149,14 @@ __device__ int read_stream_header(BitReader& br, int format, StreamResult* r)
     return PNGB200_OK;
 }
 
-// Parses a block header at the reader's position and, for compressed blocks, builds the decode
-// tables in shared memory (cooperatively, `nt` threads: 32 = calling warp, else whole CTA).
-// Returns PNGB200_OK with *type/*final/*stored_len set, PNGB200_NEED_MORE_INPUT, or an error.
-// All calling threads must hold identical reader state.
-// Stream.readBlockMetadata / readBlockTables (LZ77.InflatorBuffers.Stream.swift:59-263).
+// Block header, part 1 (ONE warp, lock step): BFINAL/BTYPE, stored LEN/NLEN, or the code lengths
+// of a fixed/dynamic block written to sh->lens (literal/length codes first, then distance codes).
+// Returns PNGB200_OK with *type/*final/*stored_len/*nlit/*ndist set, PNGB200_NEED_MORE_INPUT, or
+// an error.  Stream.readBlockMetadata / readBlockTables (LZ77.InflatorBuffers.Stream.swift:59-263).
 template <typename Shared>
-__device__ int read_block_header(BitReader& br, Shared* sh, StreamResult* r, int tid, int nt,
-                                 int* type, int* final, uint32_t* stored_len)
+__device__ int parse_block_header(BitReader& br, Shared* sh, StreamResult* r, int lane, int* type, int* final,
+                                  uint32_t* stored_len, int* nlit_out, int* ndist_out)
 {
-    auto sync = [&]() {
-        if (nt == 32) __syncwarp();
-        else __syncthreads();
-    };
     if (!br.have(3)) return PNGB200_NEED_MORE_INPUT;
     br.refill();
     uint32_t hdr = br.take(3);
@@ -180,11 +175,11 @@ __device__ int read_block_header(BitReader& br, Shared* sh, StreamResult* r, int
     }
     if (*type == 3) return fail(r, PNGB200_ERR_BLOCK_TYPE, 3);
     int nlit, ndist;
-    sync();  // previous users of the tables are done
+    __syncwarp();
     if (*type == 1) {
         nlit = 288;
         ndist = 32;
-        for (int s = tid; s < 320; s += nt)
+        for (int s = lane; s < 320; s += 32)
             sh->lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : s < 288 ? 8 : 5;
     } else {
         if (!br.have(14)) return PNGB200_NEED_MORE_INPUT;
@@ -195,20 +190,20 @@ __device__ int read_block_header(BitReader& br, Shared* sh, StreamResult* r, int
         int nclen = 4 + (int)(v >> 10);
         if (!br.have(3 * (uint64_t)nclen)) return PNGB200_NEED_MORE_INPUT;
         if (nlit > 286) return fail(r, PNGB200_ERR_RUNLITERAL_SYMBOL_COUNT, (uint32_t)nlit);
-        if (tid < 19) sh->lens[tid] = 0;
-        sync();
+        if (lane < 19) sh->lens[lane] = 0;
+        __syncwarp();
         for (int i = 0; i < nclen; ++i) {
             br.refill();
             uint32_t l = br.take(3);
-            if (tid == 0) sh->lens[c_clen_order[i]] = (uint8_t)l;
+            if (lane == 0) sh->lens[c_clen_order[i]] = (uint8_t)l;
         }
-        sync();
-        build_table<META_ROOT, META_CAP>(sh->meta, sh->lens, 19, ALPHA_META, &sh->scratch, tid, nt);
+        __syncwarp();
+        build_table<META_ROOT, META_CAP>(sh->meta, sh->lens, 19, ALPHA_META, &sh->scratch, lane, 32);
         if (sh->scratch.status) return fail(r, sh->scratch.status);
-        // code lengths: sequential, replicated in every thread; thread 0 records them
+        // code lengths: sequential, replicated in every lane; lane 0 records them
         int total = nlit + ndist, have = 0;
         uint32_t prev = 0;
-        sync();
+        __syncwarp();
         while (have < total) {
             if (!br.have(1)) return PNGB200_NEED_MORE_INPUT;
             br.refill();
@@ -217,7 +212,7 @@ __device__ int read_block_header(BitReader& br, Shared* sh, StreamResult* r, int
             if (!br.have(len)) return PNGB200_NEED_MORE_INPUT;
             if (sym < 16) {
                 br.consume((int)len);
-                if (tid == 0) sh->lens[have] = (uint8_t)sym;
+                if (lane == 0) sh->lens[have] = (uint8_t)sym;
                 prev = sym;
                 ++have;
                 continue;
@@ -234,17 +229,27 @@ __device__ int read_block_header(BitReader& br, Shared* sh, StreamResult* r, int
             if (!br.have(len + extra)) return PNGB200_NEED_MORE_INPUT;
             br.consume((int)len);
             uint32_t reps = base + br.take((int)extra);
-            if (tid == 0)
-                for (uint32_t k = 0; k < reps; ++k) sh->lens[have + k] = (uint8_t)element;
+            for (uint32_t k = lane; k < reps; k += 32) sh->lens[have + k] = (uint8_t)element;
             prev = element;
             have += (int)reps;
         }
         if (have != total) return fail(r, PNGB200_ERR_CODELENGTH_SEQUENCE);
     }
-    sync();
+    __syncwarp();
+    *nlit_out  = nlit;
+    *ndist_out = ndist;
+    return PNGB200_OK;
+}
+
+// Block header, part 2 (cooperative, `nt` threads: 32 = calling warp, else the whole CTA): the
+// literal/length and distance decode tables from sh->lens.
+template <typename Shared>
+__device__ int build_block_tables(Shared* sh, StreamResult* r, int nlit, int ndist, int tid, int nt)
+{
     build_table<LIT_ROOT, LIT_CAP>(sh->lit, sh->lens, nlit, ALPHA_LITLEN, &sh->scratch, tid, nt);
     if (sh->scratch.status) return fail(r, sh->scratch.status);
-    sync();
+    if (nt == 32) __syncwarp();
+    else __syncthreads();
     build_table<DIST_ROOT, DIST_CAP>(sh->dist, sh->lens + nlit, ndist, ALPHA_DIST, &sh->scratch, tid, nt);
     if (sh->scratch.status) return fail(r, sh->scratch.status);
     return PNGB200_OK;
@@ -300,7 +305,9 @@ __device__ void serial_inflate(SerialShared& sh, const StreamJob& job, StreamRes
     while (st == PNGB200_OK && phase == 1) {
         int      type, final;
         uint32_t stored = 0;
-        st = read_block_header(br, &sh, r, (int)lane, 32, &type, &final, &stored);
+        int nlit = 0, ndist = 0;
+        st = parse_block_header(br, &sh, r, (int)lane, &type, &final, &stored, &nlit, &ndist);
+        if (st == PNGB200_OK && type != 0) st = build_block_tables(&sh, r, nlit, ndist, (int)lane, 32);
         if (st != PNGB200_OK) break;
         if (type == 0) {
             // Stream.readBlock(upTo:), Stream.swift:384-399 -- byte-aligned copy
