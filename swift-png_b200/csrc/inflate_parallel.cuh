@@ -1,27 +1,29 @@
-// inflate_parallel.cuh -- intra-stream parallel DEFLATE inflate: one CTA (1024 threads) per stream.
+// inflate_parallel.cuh -- intra-stream parallel DEFLATE inflate: one CTA (512 threads) per stream,
+// two CTAs resident per SM so that one stream's serial stretches (header parse, fix-up rounds)
+// hide behind the other's parallel ones.
 //
 // DEFLATE has no sync markers, but Huffman codes self-synchronise: a decoder started at a wrong
-// bit offset falls into step with the true symbol sequence after a few symbols.  Per block the
-// CTA parses the header and builds the tables once (shared memory), then eats the block in WAVES
-// of 1024 subsequences x 256 bits (32 KiB of compressed data staged in shared memory, padded
+// bit offset falls into step with the true symbol sequence after a few symbols.  Per block warp 0
+// parses the header, the CTA builds the decode tables (shared memory), then the block is eaten in
+// WAVES of 512 subsequences x 256 bits (16 KiB of compressed data staged in shared memory, padded
 // 9/8 so that lane-strided word reads are bank-conflict free):
 //
-//   1. sync   every thread decodes its subsequence from a guessed start (thread 0's start is
-//             exact) and publishes the bit position where it crossed into the next subsequence;
-//             threads whose predecessor's exit differs from their start re-decode from it.  The
-//             verified prefix grows every round.  The first end-of-block symbol on the verified
-//             chain ends the wave (and the block).
-//   2. scan   a CTA-wide exclusive scan of per-thread output byte counts gives every thread its
-//             output offset.
-//   3. emit   every thread decodes its subsequence once more: literals go straight to HBM, and so
-//             do LZ77 copies whose source lies before the wave (final already -- the common case
-//             in PNG, where the distance is about one scanline).  A copy whose source is inside
-//             the wave is DEFERRED: its destination bytes are flagged in an "unresolved" bitmap
-//             (1 bit per output byte, shared memory for waves up to 256 KiB of output, HBM above)
-//             and the copy goes on a CTA-wide work list.
-//   4. resolve the work list is swept by all 1024 threads in rounds; a copy runs as soon as its
-//             source bytes carry no unresolved flag, then clears its own flags.  The number of
-//             rounds is the depth of the copy->copy dependency chain, not the number of copies.
+//   1. sync    every thread decodes its subsequence from a guessed start (thread 0's start is
+//              exact) and publishes the bit position where it crossed into the next subsequence;
+//              subsequences whose predecessor's exit differs from their start are re-decoded,
+//              compacted onto the lowest threads so a round costs only what it re-decodes.  The
+//              verified prefix grows every round; the first end-of-block symbol on the verified
+//              chain ends the wave (and the block).
+//   2. scan    a CTA-wide exclusive scan of per-subsequence output byte counts.
+//   3. emit    every thread decodes its subsequence once more; literals are written into a
+//              shared-memory image of the wave's output (32 KiB; HBM directly if the wave expands
+//              to more), every LZ77 copy becomes an item on a CTA-wide work list and its
+//              destination bytes are flagged in an "unresolved" bitmap (1 bit per output byte).
+//   4. resolve warps sweep the work list without CTA barriers: a copy runs as soon as none of its
+//              source bytes is flagged (sources behind the wave are final by construction -- the
+//              common case in PNG, where the distance is about one scanline), then clears its own
+//              flags.  Time is the depth of the copy->copy dependency chain, not the copy count.
+//   5. store   the shared-memory image goes to HBM with 16-byte coalesced stores.
 //
 // Anything unusual (invalid symbol on the verified chain, truncation, output overflow, distance
 // before the start of the output) is not handled here: warp 0 re-runs the block with the serial
@@ -38,12 +40,15 @@
 
 namespace pngb200 {
 
-constexpr int      PAR_THREADS      = 1024;
+constexpr int      PAR_THREADS      = 512;
+constexpr int      PAR_CTAS_PER_SM  = 2;
+constexpr int      PAR_WARPS        = PAR_THREADS / 32;
 constexpr uint32_t PAR_SUB_BITS     = 256;
 constexpr uint32_t PAR_SUB_WORDS    = PAR_SUB_BITS / 32;
 constexpr uint32_t PAR_WAVE_WORDS   = PAR_THREADS * PAR_SUB_WORDS + 8;
 constexpr uint32_t PAR_SMEM_WORDS   = PAR_WAVE_WORDS + PAR_WAVE_WORDS / 8 + 1;
-constexpr uint32_t PAR_BITMAP_WORDS = 8192;                        // 256 Ki output bytes per wave in smem
+constexpr uint32_t PAR_OUT_BYTES    = 32768;                         // wave output image in smem
+constexpr uint32_t PAR_BITMAP_WORDS = PAR_OUT_BYTES / 32;
 constexpr uint32_t PAR_LIST_CAP     = PAR_THREADS * (PAR_SUB_BITS / 2);  // >= copies per wave (2 bits min each)
 constexpr uint64_t PAR_MAX_WAVE_OUT = (uint64_t)PAR_LIST_CAP * 258;
 
@@ -64,10 +69,10 @@ struct ParShared {
     uint8_t      flag_[PAR_THREADS];    //                  PF_EOB / PF_BAD
     uint16_t     list_[PAR_THREADS];    // compacted ids of subsequences that must be re-decoded
     uint32_t     bitmap[PAR_BITMAP_WORDS];
+    __align__(16) uint8_t outbuf[PAR_OUT_BYTES + 32];
     uint32_t     warp_sums[32];
-    uint32_t     npend[2];
     uint32_t     first_need[2], first_stop[2], nlist[2];
-    uint32_t     anomaly, ticket;
+    uint32_t     npend, anomaly, ticket, pad;
     ParHeader    hdr;
 };
 
@@ -76,13 +81,13 @@ struct ParParams {
     StreamResult*    results;
     const uint32_t*  order;
     uint32_t*        ticket;       // global work counter (zeroed before launch)
-    uint8_t*         scratch;      // per-CTA: two copy lists + unresolved bitmap
+    uint8_t*         scratch;      // per-CTA: copy list + unresolved bitmap for oversized waves
     uint64_t         scratch_stride;
     uint64_t         bitmap_words; // size of the HBM bitmap of each CTA
     int              count;
 };
 
-struct CopyItem { uint32_t o; uint32_t run_dist; };  // run | dist << 16 ... dist 32768 -> stored as dist-1
+struct CopyItem { uint32_t o; uint32_t run_dist; };  // run | (dist - 1) << 16
 
 struct SmemBits {
     const uint32_t* w;
@@ -192,45 +197,55 @@ __device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t a, ui
     return any == 0;
 }
 
-// LZ77 copy of `run` bytes to `to` from `dist` bytes back; all needed source bytes are final
-__device__ __forceinline__ void lz_copy(uint8_t* to, uint32_t run, uint32_t dist)
+// One LZ77 copy whose needed source bytes are final.  The wave's output lives at `img` (shared
+// memory image, or the HBM destination itself); sources at negative wave offsets are read from
+// HBM at `hbm` (= destination address of wave offset 0).
+__device__ __forceinline__ void lz_copy(uint8_t* img, const uint8_t* hbm, bool img_is_hbm, uint32_t o,
+                                        uint32_t run, uint32_t dist)
 {
-    const uint8_t* from = to - dist;
-    if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
-        uint32_t k = 0;
-        for (; k + 4 <= run; k += 4) {
-            uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
-            to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3;
+    const int64_t src = (int64_t)o - (int64_t)dist;
+    uint8_t*      to  = img + o;
+    if (img_is_hbm || src >= 0 || src + (int64_t)run <= 0) {
+        const uint8_t* from = (img_is_hbm || src < 0) ? hbm + src : img + src;
+        if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
+            uint32_t k = 0;
+            for (; k + 4 <= run; k += 4) {
+                uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
+                to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3;
+            }
+            for (; k < run; ++k) to[k] = from[k];
+        } else {
+            uint32_t q = 0;
+            for (uint32_t k = 0; k < run; ++k) {
+                to[k] = from[q];
+                if (++q == dist) q = 0;
+            }
         }
-        for (; k < run; ++k) to[k] = from[k];
     } else {
-        uint32_t q = 0;
+        // source starts behind the wave (HBM) and runs into the image: byte k comes from wave
+        // offset src + k; offsets < 0 are in HBM, the rest were written earlier by this loop
         for (uint32_t k = 0; k < run; ++k) {
-            to[k] = from[q];
-            if (++q == dist) q = 0;
+            const int64_t p = src + (int64_t)k;
+            to[k] = p < 0 ? hbm[p] : img[p];
         }
     }
 }
 
-__global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParParams P)
+__global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel_kernel(ParParams P)
 {
     extern __shared__ __align__(16) unsigned char par_smem[];
     ParShared& sh = *reinterpret_cast<ParShared*>(par_smem);
     const uint32_t t    = threadIdx.x;
     const unsigned lane = lane_id(), warp = t >> 5;
-    CopyItem* const  lists[2] = {reinterpret_cast<CopyItem*>(P.scratch + blockIdx.x * P.scratch_stride),
-                                 reinterpret_cast<CopyItem*>(P.scratch + blockIdx.x * P.scratch_stride) + PAR_LIST_CAP};
-    uint32_t* const  gbitmap  = reinterpret_cast<uint32_t*>(P.scratch + blockIdx.x * P.scratch_stride +
-                                                           2 * sizeof(CopyItem) * PAR_LIST_CAP);
+    CopyItem* const list    = reinterpret_cast<CopyItem*>(P.scratch + blockIdx.x * P.scratch_stride);
+    uint32_t* const gbitmap = reinterpret_cast<uint32_t*>(P.scratch + blockIdx.x * P.scratch_stride +
+                                                         sizeof(CopyItem) * PAR_LIST_CAP);
     for (uint32_t k = t; k < PAR_BITMAP_WORDS; k += PAR_THREADS) sh.bitmap[k] = 0;
 
     for (;;) {
         __syncthreads();
         if (t == 0) {
             sh.ticket = atomicAdd(P.ticket, 1u);
-            sh.first_need[0] = sh.first_need[1] = PAR_THREADS;
-            sh.first_stop[0] = sh.first_stop[1] = PAR_THREADS;
-            sh.nlist[0] = sh.nlist[1] = 0;
             sh.anomaly = 0;
         }
         __syncthreads();
@@ -297,7 +312,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
                     for (uint32_t k = t; k < PAR_WAVE_WORDS; k += PAR_THREADS)
                         sh.words[k + (k >> 3)] = br.load_word(wbase + k);
                     if (t == 0) {
-                        sh.npend[0] = 0;
+                        sh.npend = 0;
                         sh.first_need[0] = sh.first_need[1] = PAR_THREADS;
                         sh.first_stop[0] = sh.first_stop[1] = PAR_THREADS;
                         sh.nlist[0] = sh.nlist[1] = 0;
@@ -357,9 +372,10 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
                         }
                     }
                     __syncthreads();
-                    const uint32_t my_start = sh.start_[t], ex = sh.exit_[t], n = sh.nout_[t], fl = sh.flag_[t];
+                    const uint32_t my_start = sh.start_[t], n = sh.nout_[t];
                     // ---- anomalies on the verified chain -> serial decoder ----
-                    if (t == nvalid - 1 && ((fl & PF_BAD) || (wbase << 5) + ex > br.total_bits)) sh.anomaly = 1;
+                    if (t == nvalid - 1 && ((sh.flag_[t] & PF_BAD) || (wbase << 5) + sh.exit_[t] > br.total_bits))
+                        sh.anomaly = 1;
                     // ---- scan of output counts ----
                     uint32_t mine = t < nvalid ? n : 0;
                     uint32_t incl = mine;
@@ -370,26 +386,27 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
                     if (lane == 31) sh.warp_sums[warp] = incl;
                     __syncthreads();
                     if (warp == 0) {
-                        uint32_t ws = sh.warp_sums[lane], wi = ws;
+                        uint32_t ws = lane < PAR_WARPS ? sh.warp_sums[lane] : 0, wi = ws;
                         for (int o = 1; o < 32; o <<= 1) {
                             uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
                             if ((int)lane >= o) wi += v;
                         }
-                        sh.warp_sums[lane] = wi - ws;  // exclusive
+                        if (lane < PAR_WARPS) sh.warp_sums[lane] = wi - ws;  // exclusive
+                        if (lane == PAR_WARPS - 1) sh.warp_sums[PAR_WARPS] = wi;  // wave total
                     }
                     __syncthreads();
                     const uint32_t o_start = sh.warp_sums[warp] + incl - mine;
-                    __syncthreads();
-                    if (t == PAR_THREADS - 1) sh.warp_sums[0] = o_start + mine;  // wave total
-                    __syncthreads();
-                    const uint32_t total = sh.warp_sums[0];
+                    const uint32_t total   = sh.warp_sums[PAR_WARPS];
                     if (sh.anomaly || out + total > job.dst_cap || total > P.bitmap_words * 32) {
                         fallback = true;
                         break;
                     }
-                    // ---- emit: literals + copies from behind the wave; defer in-wave copies ----
-                    uint8_t* const  wdst = dst + out;
-                    uint32_t* const U    = total <= PAR_BITMAP_WORDS * 32 ? sh.bitmap : gbitmap;
+                    // ---- emit: literals into the output image, copies onto the work list ----
+                    uint8_t* const  wdst   = dst + out;           // HBM address of wave offset 0
+                    const uint32_t  shift  = (uint32_t)((uintptr_t)wdst & 15);
+                    const bool      in_hbm = total > PAR_OUT_BYTES;
+                    uint8_t* const  img    = in_hbm ? wdst : sh.outbuf + shift;
+                    uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
                     if (t < nvalid) {
                         SmemBits b;
                         b.init(sh.words, my_start);
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
                             uint32_t kind = e_kind(e);
                             if (kind == K_LIT) {
                                 b.consume(e_len(e));
-                                wdst[o++] = (uint8_t)e_value(e);
+                                img[o++] = (uint8_t)e_value(e);
                             } else if (kind == K_BASE) {
                                 b.consume(e_len(e));
                                 uint32_t run = e_value(e) + b.take(e_extra(e));
@@ -412,13 +429,8 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
                                     sh.anomaly = 1;
                                     break;
                                 }
-                                if ((int64_t)o - (int64_t)dist + (int64_t)min(run, dist) <= 0) {
-                                    lz_copy(wdst + o, run, dist);  // source entirely behind the wave
-                                } else {
-                                    bits_set(U, o, o + run);
-                                    uint32_t slot = atomicAdd(&sh.npend[0], 1u);
-                                    lists[0][slot] = CopyItem{o, run | (dist - 1) << 16};
-                                }
+                                bits_set(U, o, o + run);
+                                list[atomicAdd(&sh.npend, 1u)] = CopyItem{o, run | (dist - 1) << 16};
                                 o += run;
                             } else {
                                 break;  // end of block
@@ -427,38 +439,60 @@ __global__ void __launch_bounds__(PAR_THREADS, 1) inflate_parallel_kernel(ParPar
                     }
                     __threadfence_block();
                     __syncthreads();
-                    // ---- resolve deferred copies in dependency order ----
-                    uint32_t cur = 0;
-                    while (!sh.anomaly) {
-                        const uint32_t np = sh.npend[cur];
-                        if (np == 0) break;
-                        ++resolve_rounds;
-                        __syncthreads();
-                        if (t == 0) sh.npend[cur ^ 1] = 0;
-                        __syncthreads();
-                        for (uint32_t i = t; i < np; i += PAR_THREADS) {
-                            const CopyItem it = lists[cur][i];
-                            const uint32_t run = it.run_dist & 0xffff, dist = (it.run_dist >> 16) + 1;
-                            const int64_t  src = (int64_t)it.o - (int64_t)dist;
-                            const uint32_t a = (uint32_t)max(src, (int64_t)0);
-                            const uint32_t c = (uint32_t)(src + (int64_t)min(run, dist));
-                            if (bits_all_clear(U, a, c)) {
-                                lz_copy(wdst + it.o, run, dist);
-                                __threadfence_block();
-                                bits_clear(U, it.o, it.o + run);
-                            } else {
-                                lists[cur ^ 1][atomicAdd(&sh.npend[cur ^ 1], 1u)] = it;
+                    // ---- resolve: each warp sweeps its share of the list; no CTA barriers ----
+                    const uint32_t np = sh.npend;
+                    if (!sh.anomaly && np) {
+                        // a lane owns items t, t + 512, ...; it retries the ones whose sources are not
+                        // final yet on the next pass (the earliest open copy of the wave is always
+                        // ready, so every pass makes progress somewhere in the CTA)
+                        bool left = true;
+                        while (__any_sync(0xffffffffu, left)) {
+                            left = false;
+                            bool progressed = false;
+                            for (uint32_t idx = t; idx < np; idx += PAR_THREADS) {
+                                const CopyItem it = list[idx];
+                                if (it.run_dist == 0) continue;  // done on an earlier pass
+                                const uint32_t run = it.run_dist & 0xffff, dist = (it.run_dist >> 16) + 1;
+                                const int64_t  src = (int64_t)it.o - (int64_t)dist;
+                                const int64_t  hi  = src + (int64_t)min(run, dist);
+                                bool ready = true;
+                                if (hi > 0) ready = bits_all_clear(U, (uint32_t)max(src, (int64_t)0), (uint32_t)hi);
+                                if (ready) {
+                                    lz_copy(img, wdst, in_hbm, it.o, run, dist);
+                                    __threadfence_block();
+                                    bits_clear(U, it.o, it.o + run);
+                                    list[idx].run_dist = 0;
+                                    progressed = true;
+                                } else {
+                                    left = true;
+                                }
                             }
+                            ++resolve_rounds;
+                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(100);
                         }
-                        __threadfence_block();
-                        __syncthreads();
-                        cur ^= 1;
                     }
+                    __threadfence_block();
+                    __syncthreads();
                     if (sh.anomaly) {
                         // leave the bitmap clean for whoever uses it next
                         for (uint32_t k = t; k < (total + 31) / 32; k += PAR_THREADS) U[k] = 0;
                         fallback = true;
                         break;
+                    }
+                    // ---- store: shared-memory image -> HBM, 16-byte coalesced ----
+                    if (!in_hbm && total) {
+                        uint8_t* const       base = wdst - shift;            // 16-byte aligned
+                        const uint32_t       end  = shift + total;           // bytes [shift, end) are ours
+                        const uint32_t       nq   = (end + 15) >> 4;
+                        const uint4* const   q    = reinterpret_cast<const uint4*>(sh.outbuf);
+                        for (uint32_t c = t; c < nq; c += PAR_THREADS) {
+                            const uint32_t lo = c << 4, hi = lo + 16;
+                            if (lo >= shift && hi <= end) {
+                                reinterpret_cast<uint4*>(base)[c] = q[c];
+                            } else {
+                                for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) base[k] = sh.outbuf[k];
+                            }
+                        }
                     }
                     out += total;
                     br.seek((wbase << 5) + sh.exit_[nvalid - 1]);
@@ -511,7 +545,7 @@ inline uint64_t par_bitmap_words(uint64_t max_dst_cap)
 }
 inline uint64_t par_scratch_stride(uint64_t bitmap_words)
 {
-    uint64_t s = 2 * sizeof(CopyItem) * (uint64_t)PAR_LIST_CAP + 4 * bitmap_words;
+    uint64_t s = sizeof(CopyItem) * (uint64_t)PAR_LIST_CAP + 4 * bitmap_words;
     return (s + 255) / 256 * 256;
 }
 

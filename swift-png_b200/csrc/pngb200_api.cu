@@ -171,7 +171,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             ParParams pp;
             pp.bitmap_words = par_bitmap_words(max_cap);
             pp.scratch_stride = par_scratch_stride(pp.bitmap_words);
-            unsigned grid = (unsigned)std::min<size_t>(par.size(), (size_t)ctx->sm_count);
+            unsigned grid = (unsigned)std::min<size_t>(par.size(), (size_t)ctx->sm_count * PAR_CTAS_PER_SM);
             size_t need = (size_t)pp.scratch_stride * grid + 256;
             if (need > ctx->d_scratch.cap) {  // fresh scratch must start zeroed (the kernel keeps it clean)
                 CU(ctx->d_scratch.reserve(need));
