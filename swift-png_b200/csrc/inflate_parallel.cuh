@@ -66,11 +66,12 @@ struct ParShared {
     uint32_t     start_[PAR_THREADS];   // per subsequence: decode start (wave-relative bit)
     uint32_t     exit_[PAR_THREADS];    //                  first symbol boundary past its end
     uint32_t     nout_[PAR_THREADS];    //                  output bytes
+    uint16_t     ncopy_[PAR_THREADS];   //                  LZ77 copies
     uint8_t      flag_[PAR_THREADS];    //                  PF_EOB / PF_BAD
     uint16_t     list_[PAR_THREADS];    // compacted ids of subsequences that must be re-decoded
     uint32_t     bitmap[PAR_BITMAP_WORDS];
     __align__(16) uint8_t outbuf[PAR_OUT_BYTES + 32];
-    uint32_t     warp_sums[32];
+    uint64_t     warp_sums[32];
     uint32_t     first_need[2], first_stop[2], nlist[2];
     uint32_t     npend, anomaly, ticket, pad;
     ParHeader    hdr;
@@ -133,11 +134,13 @@ struct SmemBits {
 
 // sync-phase decode: symbol boundaries and output byte count only
 __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t start, uint32_t limit,
-                                                 uint32_t& exit_bit, uint32_t& nout, uint32_t& flags)
+                                                 uint32_t& exit_bit, uint32_t& nout, uint32_t& ncopy,
+                                                 uint32_t& flags)
 {
     SmemBits b;
     b.init(sh.words, start);
     nout  = 0;
+    ncopy = 0;
     flags = 0;
     while (b.pos < limit) {
         b.refill();
@@ -154,6 +157,7 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
             if (e_kind(d) != K_BASE) { flags = PF_BAD; break; }
             b.consume(e_len(d) + e_extra(d));
             nout += run;
+            ++ncopy;
         } else if (kind == K_EOB) {
             b.consume(e_len(e));
             flags = PF_EOB;
@@ -321,11 +325,12 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     const uint32_t rel0  = (uint32_t)(wstart - (wbase << 5));  // < 256
                     const uint32_t limit = (t + 1) * PAR_SUB_BITS;
                     {
-                        uint32_t s0 = t == 0 ? rel0 : t * PAR_SUB_BITS, ex0, n0, fl0;
-                        par_decode_count(sh, s0, limit, ex0, n0, fl0);
+                        uint32_t s0 = t == 0 ? rel0 : t * PAR_SUB_BITS, ex0, n0, c0, fl0;
+                        par_decode_count(sh, s0, limit, ex0, n0, c0, fl0);
                         sh.start_[t] = s0;
                         sh.exit_[t]  = ex0;
                         sh.nout_[t]  = n0;
+                        sh.ncopy_[t] = (uint16_t)c0;
                         sh.flag_[t]  = (uint8_t)fl0;
                     }
                     // ---- sync rounds: only subsequences whose start moved are re-decoded, compacted
@@ -364,11 +369,12 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         const uint32_t cnt = sh.nlist[p];
                         if (t < cnt) {
                             const uint32_t u = sh.list_[t];
-                            uint32_t ex0, n0, fl0;
-                            par_decode_count(sh, sh.start_[u], (u + 1) * PAR_SUB_BITS, ex0, n0, fl0);
-                            sh.exit_[u] = ex0;
-                            sh.nout_[u] = n0;
-                            sh.flag_[u] = (uint8_t)fl0;
+                            uint32_t ex0, n0, c0, fl0;
+                            par_decode_count(sh, sh.start_[u], (u + 1) * PAR_SUB_BITS, ex0, n0, c0, fl0);
+                            sh.exit_[u]  = ex0;
+                            sh.nout_[u]  = n0;
+                            sh.ncopy_[u] = (uint16_t)c0;
+                            sh.flag_[u]  = (uint8_t)fl0;
                         }
                     }
                     __syncthreads();
@@ -376,27 +382,30 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     // ---- anomalies on the verified chain -> serial decoder ----
                     if (t == nvalid - 1 && ((sh.flag_[t] & PF_BAD) || (wbase << 5) + sh.exit_[t] > br.total_bits))
                         sh.anomaly = 1;
-                    // ---- scan of output counts ----
-                    uint32_t mine = t < nvalid ? n : 0;
-                    uint32_t incl = mine;
+                    // ---- scan of output byte counts and copy counts (packed: copies << 40 | bytes) ----
+                    const uint64_t mine = t < nvalid ? ((uint64_t)sh.ncopy_[t] << 40 | n) : 0;
+                    uint64_t incl = mine;
                     for (int o = 1; o < 32; o <<= 1) {
-                        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                        uint64_t v = __shfl_up_sync(0xffffffffu, incl, o);
                         if ((int)lane >= o) incl += v;
                     }
                     if (lane == 31) sh.warp_sums[warp] = incl;
                     __syncthreads();
                     if (warp == 0) {
-                        uint32_t ws = lane < PAR_WARPS ? sh.warp_sums[lane] : 0, wi = ws;
+                        uint64_t ws = lane < PAR_WARPS ? sh.warp_sums[lane] : 0, wi = ws;
                         for (int o = 1; o < 32; o <<= 1) {
-                            uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+                            uint64_t v = __shfl_up_sync(0xffffffffu, wi, o);
                             if ((int)lane >= o) wi += v;
                         }
                         if (lane < PAR_WARPS) sh.warp_sums[lane] = wi - ws;  // exclusive
-                        if (lane == PAR_WARPS - 1) sh.warp_sums[PAR_WARPS] = wi;  // wave total
+                        if (lane == PAR_WARPS - 1) sh.warp_sums[PAR_WARPS] = wi;  // wave totals
                     }
                     __syncthreads();
-                    const uint32_t o_start = sh.warp_sums[warp] + incl - mine;
-                    const uint32_t total   = sh.warp_sums[PAR_WARPS];
+                    const uint64_t excl    = sh.warp_sums[warp] + incl - mine;
+                    const uint32_t o_start = (uint32_t)(excl & 0xffffffffffull);
+                    uint32_t       c_next  = (uint32_t)(excl >> 40);           // my first list slot
+                    const uint32_t total   = (uint32_t)(sh.warp_sums[PAR_WARPS] & 0xffffffffffull);
+                    const uint32_t np      = (uint32_t)(sh.warp_sums[PAR_WARPS] >> 40);
                     if (sh.anomaly || out + total > job.dst_cap || total > P.bitmap_words * 32) {
                         fallback = true;
                         break;
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                                     break;
                                 }
                                 bits_set(U, o, o + run);
-                                list[atomicAdd(&sh.npend, 1u)] = CopyItem{o, run | (dist - 1) << 16};
+                                list[c_next++] = CopyItem{o, run | (dist - 1) << 16};  // list is sorted by o
                                 o += run;
                             } else {
                                 break;  // end of block
@@ -439,19 +448,21 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     }
                     __threadfence_block();
                     __syncthreads();
-                    // ---- resolve: each warp sweeps its share of the list; no CTA barriers ----
-                    const uint32_t np = sh.npend;
+                    // ---- resolve: no CTA barriers.  The list is sorted by output offset and a copy only
+                    //      depends on smaller offsets, so a lane may simply block on its current item
+                    //      (items t, t + 512, ... in order): the smallest open item is always ready ----
                     if (!sh.anomaly && np) {
-                        // a lane owns items t, t + 512, ...; it retries the ones whose sources are not
-                        // final yet on the next pass (the earliest open copy of the wave is always
-                        // ready, so every pass makes progress somewhere in the CTA)
-                        bool left = true;
-                        while (__any_sync(0xffffffffu, left)) {
-                            left = false;
+                        uint32_t idx  = t;
+                        CopyItem it   = CopyItem{0, 0};
+                        bool     have = false;
+                        for (;;) {
+                            if (!have && idx < np) {
+                                it   = list[idx];
+                                idx += PAR_THREADS;
+                                have = true;
+                            }
                             bool progressed = false;
-                            for (uint32_t idx = t; idx < np; idx += PAR_THREADS) {
-                                const CopyItem it = list[idx];
-                                if (it.run_dist == 0) continue;  // done on an earlier pass
+                            if (have) {
                                 const uint32_t run = it.run_dist & 0xffff, dist = (it.run_dist >> 16) + 1;
                                 const int64_t  src = (int64_t)it.o - (int64_t)dist;
                                 const int64_t  hi  = src + (int64_t)min(run, dist);
@@ -461,14 +472,13 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                                     lz_copy(img, wdst, in_hbm, it.o, run, dist);
                                     __threadfence_block();
                                     bits_clear(U, it.o, it.o + run);
-                                    list[idx].run_dist = 0;
+                                    have = false;
                                     progressed = true;
-                                } else {
-                                    left = true;
                                 }
                             }
                             ++resolve_rounds;
-                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(100);
+                            if (!__any_sync(0xffffffffu, have || idx < np)) break;
+                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(40);
                         }
                     }
                     __threadfence_block();
