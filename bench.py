@@ -32,7 +32,7 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (width, height, sixteen, default batch per GPU, default unique images)
-    "8k-rgba8": (7680, 4320, False, 148, 2),
+    "8k-rgba8": (7680, 4320, False, 296, 2),
     "1080p-rgba8": (1920, 1080, False, 1024, 16),
     "8k-rgba16": (7680, 4320, True, 8, 2),
     "small": (512, 512, False, 64, 4),
@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--level", type=int, default=6, help="zlib level of the input streams")
     ap.add_argument("--inflate-mode", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: <= 8 GB pinned)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=0)
     return ap.parse_args()
@@ -201,12 +202,15 @@ def main():
     npix = w * h
     storage_bytes = npix * bpp
 
-    # device-resident inputs (unique streams, referenced by many jobs) and outputs
-    d_idat = [torch.frombuffer(bytearray(it["idat"]), dtype=torch.uint8).cuda() for it in items]
+    # device-resident inputs -- one private copy of its stream per job, so the compressed bytes of a
+    # step (several GB) cannot sit in the 126 MB L2 -- and outputs
+    d_unique = [torch.frombuffer(bytearray(it["idat"]), dtype=torch.uint8).cuda() for it in items]
+    d_idat = [d_unique[i % len(items)].clone() for i in range(B)]
+    del d_unique
     d_pixels = torch.empty((B, storage_bytes), dtype=torch.uint8, device="cuda")
     descs = (pkg.ImageDesc * B)()
     for i in range(B):
-        u = i % len(items)
+        u = i
         descs[i].idat = d_idat[u].data_ptr()
         descs[i].idat_len = d_idat[u].numel()
         descs[i].pixels = d_pixels[i].data_ptr()
@@ -216,9 +220,18 @@ def main():
         descs[i].interlaced, descs[i].format = 0, 0
     L = ctx._lib
 
+    status_words = torch.zeros((B, 2), dtype=torch.int64, device="cuda")
+    gathered = [torch.empty_like(status_words) for _ in range(world)] if world > 1 else None
+
     def step_device():
         ctx.check(L.pngb200_decode_batch_enqueue(ctx.handle, descs, B, pkg.MEM_DEVICE))
         ctx.check(L.pngb200_decode_batch_finish(ctx.handle, descs, B))
+        if world > 1:
+            # the only collective of the path: every rank learns the whole batch's per-image
+            # (status, adler32) words; decoded pixels stay sharded on the GPU that produced them
+            status_words.copy_(torch.tensor([[descs[i].status, descs[i].checksum] for i in range(B)],
+                                            dtype=torch.int64), non_blocking=True)
+            dist.all_gather(gathered, status_words)
 
     def barrier():
         if world > 1:
@@ -263,7 +276,7 @@ def main():
         import psutil
         per_image = storage_bytes + max(len(it["idat"]) for it in items)
         avail = psutil.virtual_memory().available
-        EB = B
+        EB = min(B, args.e2e_batch) if args.e2e_batch else (B if per_image * B < (8 << 30) else max(8, (8 << 30) // per_image))
         while EB > 8 and EB * per_image * 2.5 * max(world, 1) > avail:
             EB //= 2  # pinned host staging for the whole batch must fit comfortably in host RAM
         full_B, B = B, EB

@@ -19,6 +19,8 @@ import importlib.util
 import os
 from dataclasses import dataclass
 
+from . import shard  # noqa: F401  (multi-GPU partitioning helpers)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpngb200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "pngb200.h")
