@@ -103,6 +103,9 @@ def lib():
             L.orc_deflate.restype = C.c_size_t
             L.orc_deflate_bound.argtypes = [C.c_size_t]
             L.orc_deflate_bound.restype = C.c_size_t
+            L.orc_debug_greedy_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_long, C.c_int,
+                                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_size_t]
+            L.orc_debug_greedy_parse.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -171,3 +174,11 @@ def deflate(data: bytes, level: int = 9, fmt: int = ZLIB, exponent: int = 15) ->
     n = L.orc_deflate(fmt, level, exponent, data, len(data), buf, cap)
     assert n != C.c_size_t(-1).value
     return buf.raw[:n]
+
+
+def greedy_parse(data: bytes, exponent: int, attempts: int = 2 ** 62, goal: int = 2 ** 30):
+    """[(run, distance)] of the greedy segmentation (test hook for the reference's Matching KAT)."""
+    n = len(data)
+    runs, dists = (C.c_int * (n + 8))(), (C.c_int * (n + 8))()
+    k = lib().orc_debug_greedy_parse(data, n, exponent, attempts, goal, runs, dists, n + 8)
+    return [(runs[i], dists[i]) for i in range(k)]
