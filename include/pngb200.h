@@ -167,6 +167,46 @@ typedef struct pngb200_filter_desc {
 
 int pngb200_filter_batch(pngb200_ctx* ctx, pngb200_filter_desc* images, size_t count, int memspace);
 
+/* Encode-side stage 2: LZ77.Deflator(format:level:exponent:hint:).push(src, last: true) and the
+ * concatenation of every pull() -- the reference's compressed bytes, bit for bit (its output does
+ * not depend on push granularity or on `hint`).  Replaces Sources/LZ77/Deflator/LZ77.Deflator.swift:8-44,
+ * Sources/LZ77/Gzip/Gzip.swift:34-46 (Gzip.archive) and everything behind them.  level 0...13 as in
+ * LZ77.DeflatorSearch (0-3 greedy, 4-7 lazy, 8-13 full); exponent 8...15. */
+typedef struct pngb200_deflate_desc {
+    const uint8_t* src;
+    size_t         src_len;
+    uint8_t*       dst;
+    size_t         dst_cap;   /* pngb200_deflate_bound(src_len) is always enough */
+    int32_t        format;    /* pngb200_format */
+    int32_t        level;
+    int32_t        exponent;
+    /* results */
+    int32_t        status;
+    uint32_t       checksum;  /* Adler-32 / CRC-32 of src as written into the trailer */
+    uint32_t       blocks;
+    uint64_t       produced;
+} pngb200_deflate_desc;
+
+int    pngb200_deflate_batch(pngb200_ctx* ctx, pngb200_deflate_desc* streams, size_t count, int memspace);
+size_t pngb200_deflate_bound(size_t src_len);
+
+/* PNG.Encoder.pull over a whole image: collect + filter + deflate (format .zlib / .ios) -> the
+ * concatenated IDAT payload.  Replaces Sources/PNG/Encoding/PNG.Encoder.swift:33-129. */
+typedef struct pngb200_encode_desc {
+    const uint8_t* pixels;    /* PNG.Image.storage */
+    size_t         pixels_len;
+    uint8_t*       idat;      /* out: concatenated IDAT payload */
+    size_t         idat_cap;
+    uint32_t       width, height;
+    uint8_t        volume, depth, interlaced, format;
+    int32_t        level;
+    int32_t        status;
+    uint32_t       checksum, blocks;
+    uint64_t       produced;
+} pngb200_encode_desc;
+
+int pngb200_encode_batch(pngb200_ctx* ctx, pngb200_encode_desc* images, size_t count, int memspace);
+
 /* size helpers (host arithmetic only) */
 size_t pngb200_filtered_size(uint32_t width, uint32_t height, int volume, int interlaced);
 size_t pngb200_storage_size(uint32_t width, uint32_t height, int volume);

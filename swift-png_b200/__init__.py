@@ -90,6 +90,27 @@ class FilterDesc(C.Structure):
     ]
 
 
+class DeflateDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src_len", C.c_size_t),
+        ("dst", C.c_void_p), ("dst_cap", C.c_size_t),
+        ("format", C.c_int32), ("level", C.c_int32), ("exponent", C.c_int32),
+        ("status", C.c_int32), ("checksum", C.c_uint32), ("blocks", C.c_uint32),
+        ("produced", C.c_uint64),
+    ]
+
+
+class EncodeDesc(C.Structure):
+    _fields_ = [
+        ("pixels", C.c_void_p), ("pixels_len", C.c_size_t),
+        ("idat", C.c_void_p), ("idat_cap", C.c_size_t),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("volume", C.c_uint8), ("depth", C.c_uint8), ("interlaced", C.c_uint8), ("format", C.c_uint8),
+        ("level", C.c_int32), ("status", C.c_int32), ("checksum", C.c_uint32), ("blocks", C.c_uint32),
+        ("produced", C.c_uint64),
+    ]
+
+
 class PNGB200Error(RuntimeError):
     def __init__(self, status: int, message: str = ""):
         super().__init__(f"pngb200 status {status}: {message}")
@@ -143,6 +164,12 @@ def lib():
     L.pngb200_decode_batch_finish.restype = C.c_int
     L.pngb200_filter_batch.argtypes = [C.c_void_p, C.POINTER(FilterDesc), C.c_size_t, C.c_int]
     L.pngb200_filter_batch.restype = C.c_int
+    L.pngb200_deflate_batch.argtypes = [C.c_void_p, C.POINTER(DeflateDesc), C.c_size_t, C.c_int]
+    L.pngb200_deflate_batch.restype = C.c_int
+    L.pngb200_deflate_bound.argtypes = [C.c_size_t]
+    L.pngb200_deflate_bound.restype = C.c_size_t
+    L.pngb200_encode_batch.argtypes = [C.c_void_p, C.POINTER(EncodeDesc), C.c_size_t, C.c_int]
+    L.pngb200_encode_batch.restype = C.c_int
     L.pngb200_filtered_size.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int]
     L.pngb200_filtered_size.restype = C.c_size_t
     L.pngb200_storage_size.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
@@ -347,6 +374,65 @@ def filter_batch(ctx: Context, images):
         descs[i].volume, descs[i].depth, descs[i].interlaced = vol, g["depth"], int(il)
     ctx.check(ctx._lib.pngb200_filter_batch(ctx.handle, descs, n, MEM_HOST))
     return [keep[i][1].raw[: keep[i][2]] for i in range(n)]
+
+
+def deflate_batch(ctx: Context, streams, level: int = 9, fmt: int = FORMAT_ZLIB, exponent: int = 15):
+    """LZ77.Deflator(format:level:exponent:).push(data, last: true) + all pull()s, per stream.
+    `level` / `fmt` may be ints or per-stream sequences.  Returns list of (status, bytes)."""
+    streams = list(streams)
+    n = len(streams)
+    descs = (DeflateDesc * n)()
+    keep = []
+    for i, data in enumerate(streams):
+        data = bytes(data)
+        cap = ctx._lib.pngb200_deflate_bound(len(data))
+        src = C.create_string_buffer(data, len(data)) if len(data) else C.create_string_buffer(1)
+        dst = C.create_string_buffer(cap)
+        keep.append((src, dst))
+        descs[i].src = _buf_addr(src)
+        descs[i].src_len = len(data)
+        descs[i].dst = _buf_addr(dst)
+        descs[i].dst_cap = cap
+        descs[i].format = fmt if isinstance(fmt, int) else fmt[i]
+        descs[i].level = level if isinstance(level, int) else level[i]
+        descs[i].exponent = exponent if isinstance(exponent, int) else exponent[i]
+    ctx.check(ctx._lib.pngb200_deflate_batch(ctx.handle, descs, n, MEM_HOST))
+    return [(descs[i].status, keep[i][1].raw[: descs[i].produced]) for i in range(n)]
+
+
+def gzip_archive(ctx: Context, data: bytes, level: int = 7) -> bytes:
+    """Gzip.archive(bytes:level:)"""
+    (st, out), = deflate_batch(ctx, [data], level, FORMAT_GZIP)
+    if st != OK:
+        raise PNGB200Error(st, "gzip_archive")
+    return out
+
+
+def encode_batch(ctx: Context, images, level: int = 9):
+    """PNG.Encoder over a batch: storage -> concatenated IDAT payload (filter select + deflate).
+    `images`: dicts with pixels, width, height, volume, depth, interlaced, fmt."""
+    images = list(images)
+    n = len(images)
+    descs = (EncodeDesc * n)()
+    keep = []
+    for i, g in enumerate(images):
+        px = bytes(g["pixels"])
+        w, h, vol = g["width"], g["height"], g["volume"]
+        il = bool(g.get("interlaced", False))
+        cap = ctx._lib.pngb200_deflate_bound(filtered_size(w, h, vol, il))
+        src = C.create_string_buffer(px, len(px))
+        dst = C.create_string_buffer(cap)
+        keep.append((src, dst))
+        descs[i].pixels = _buf_addr(src)
+        descs[i].pixels_len = len(px)
+        descs[i].idat = _buf_addr(dst)
+        descs[i].idat_cap = cap
+        descs[i].width, descs[i].height = w, h
+        descs[i].volume, descs[i].depth, descs[i].interlaced = vol, g["depth"], int(il)
+        descs[i].format = g.get("fmt", FORMAT_ZLIB)
+        descs[i].level = g.get("level", level)
+    ctx.check(ctx._lib.pngb200_encode_batch(ctx.handle, descs, n, MEM_HOST))
+    return [(descs[i].status, keep[i][1].raw[: descs[i].produced]) for i in range(n)]
 
 
 class Inflator:

@@ -13,6 +13,7 @@
 
 #include "checksum.cuh"
 #include "common.cuh"
+#include "deflate.cuh"
 #include "filter.cuh"
 #include "inflate_parallel.cuh"
 #include "inflate_serial.cuh"
@@ -91,7 +92,7 @@ struct pngb200_ctx {
     bool         pending = false;
     int          pending_memspace = 0;
     // device workspaces (grow-only)
-    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order, d_scratch;
+    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order, d_scratch, d_dfscratch, d_dfjobs, d_dfres, d_enc;
     // pinned host tables
     PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order;
     size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
@@ -384,6 +385,11 @@ pngb200_ctx* pngb200_ctx_create(int device)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     DeviceGuard guard(device);
+    if (cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)) != cudaSuccess) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(DfShared));
+        delete ctx;
+        return nullptr;
+    }
     if (configure_inflate_parallel() != 0) {
         set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(ParShared));
         delete ctx;
@@ -404,7 +410,8 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->d_jobs, &ctx->d_results, &ctx->d_imgjobs, &ctx->d_genjobs, &ctx->d_misc,
-                      &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_order, &ctx->d_scratch})
+                      &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_order, &ctx->d_scratch, &ctx->d_dfscratch,
+                      &ctx->d_dfjobs, &ctx->d_dfres, &ctx->d_enc})
         b->release();
     for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order})
         b->release();
@@ -758,6 +765,162 @@ int pngb200_filter_batch(pngb200_ctx* ctx, pngb200_filter_desc* im, size_t count
     return PNGB200_OK;
 }
 
+}  // extern "C"
+
+// ---------------- encode stage 2: deflate ----------------
+namespace {
+// device-resident jobs -> compressed streams (results stay in d_dfres / are copied to `hres`)
+int run_deflate(pngb200_ctx* ctx, const std::vector<DeflateJob>& jobs, DeflateResult* hres)
+{
+    size_t count = jobs.size();
+    uint64_t verts = 2;
+    for (const DeflateJob& j : jobs)
+        if (j.level >= 8) verts = std::max<uint64_t>(verts, std::min<uint64_t>(j.n, DF_GRAPH_CAP) + 2);
+    uint64_t stride = df_scratch_stride(verts);
+    uint64_t budget = 48ull << 30;
+    size_t slots = std::min<size_t>({count, (size_t)std::max<uint64_t>(1, budget / stride), (size_t)ctx->sm_count * 8});
+    CU(ctx->d_dfscratch.reserve(stride * slots + 256));
+    CU(ctx->d_dfjobs.reserve(sizeof(DeflateJob) * count));
+    CU(ctx->d_dfres.reserve(sizeof(DeflateResult) * count));
+    CU(cudaMemcpyAsync(ctx->d_dfjobs.p, jobs.data(), sizeof(DeflateJob) * count, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_dfres.p, 0, sizeof(DeflateResult) * count, ctx->stream));
+    DfParams P;
+    P.jobs = ctx->d_dfjobs.as<DeflateJob>();
+    P.results = ctx->d_dfres.as<DeflateResult>();
+    P.scratch = ctx->d_dfscratch.as<uint8_t>();
+    P.scratch_stride = stride;
+    P.graph_vertices = verts;
+    P.ticket = (uint32_t*)(ctx->d_dfscratch.as<uint8_t>() + stride * slots);
+    P.count = (int)count;
+    CU(cudaMemsetAsync(P.ticket, 0, sizeof(uint32_t), ctx->stream));
+    deflate_kernel<<<(unsigned)slots, 32, sizeof(DfShared), ctx->stream>>>(P);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hres, ctx->d_dfres.p, sizeof(DeflateResult) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PNGB200_OK;
+}
+}  // namespace
+
+extern "C" size_t pngb200_deflate_bound(size_t n) { return n + n / 2 + 4096; }
+
+extern "C" int pngb200_deflate_batch(pngb200_ctx* ctx, pngb200_deflate_desc* s, size_t count, int memspace)
+{
+    if (!ctx || (!s && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is pending");
+    if (count == 0) return PNGB200_OK;
+    DeviceGuard guard(ctx->device);
+    const bool host = memspace == PNGB200_MEM_HOST;
+    std::vector<DeflateJob> jobs(count);
+    std::vector<size_t> in_off(count), out_off(count);
+    size_t in_total = 0, out_total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        if ((!s[i].src && s[i].src_len) || !s[i].dst || s[i].format < 0 || s[i].format > 2 || s[i].exponent < 8 ||
+            s[i].exponent > 15)
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "stream %zu: bad descriptor", i);
+        in_off[i] = in_total;
+        out_off[i] = out_total;
+        in_total += align_up(s[i].src_len + 16, 256);
+        out_total += align_up(s[i].dst_cap + 16, 256);
+    }
+    if (host) {
+        CU(ctx->d_in.reserve(in_total));
+        CU(ctx->d_out.reserve(out_total));
+        for (size_t i = 0; i < count; ++i)
+            if (s[i].src_len)
+                CU(cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + in_off[i], s[i].src, s[i].src_len,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (size_t i = 0; i < count; ++i) {
+        jobs[i].src = host ? ctx->d_in.as<uint8_t>() + in_off[i] : s[i].src;
+        jobs[i].n = s[i].src_len;
+        jobs[i].dst = host ? ctx->d_out.as<uint8_t>() + out_off[i] : s[i].dst;
+        jobs[i].cap = s[i].dst_cap;
+        jobs[i].format = s[i].format;
+        jobs[i].level = s[i].level;
+        jobs[i].exponent = s[i].exponent;
+        jobs[i].pad = 0;
+    }
+    std::vector<DeflateResult> res(count);
+    int rc = run_deflate(ctx, jobs, res.data());
+    if (rc != PNGB200_OK) return rc;
+    for (size_t i = 0; i < count; ++i) {
+        s[i].status = res[i].status;
+        s[i].checksum = res[i].checksum;
+        s[i].blocks = res[i].blocks;
+        s[i].produced = res[i].produced;
+        if (host && res[i].status == PNGB200_OK && res[i].produced)
+            CU(cudaMemcpyAsync(s[i].dst, ctx->d_out.as<uint8_t>() + out_off[i], res[i].produced,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PNGB200_OK;
+}
+
+extern "C" int pngb200_encode_batch(pngb200_ctx* ctx, pngb200_encode_desc* im, size_t count, int memspace)
+{
+    if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (count == 0) return PNGB200_OK;
+    DeviceGuard guard(ctx->device);
+    const bool host = memspace == PNGB200_MEM_HOST;
+    // stage 1: filter into a private device workspace (device memspace of the filter entry point)
+    std::vector<pngb200_filter_desc> fd(count);
+    std::vector<size_t> f_off(count), p_off(count), o_off(count);
+    size_t f_total = 0, p_total = 0, o_total = 0;
+    for (size_t i = 0; i < count; ++i) {
+        size_t fsz = pngb200_filtered_size(im[i].width, im[i].height, im[i].volume, im[i].interlaced);
+        f_off[i] = f_total;
+        f_total += align_up(fsz + 16, 256);
+        p_off[i] = p_total;
+        p_total += align_up(im[i].pixels_len + 16, 256);
+        o_off[i] = o_total;
+        o_total += align_up(im[i].idat_cap + 16, 256);
+    }
+    CU(ctx->d_enc.reserve(f_total + (host ? p_total + o_total : 0) + 256));
+    uint8_t* d_f = ctx->d_enc.as<uint8_t>();
+    uint8_t* d_p = d_f + f_total;
+    uint8_t* d_o = d_p + (host ? p_total : 0);
+    for (size_t i = 0; i < count; ++i) {
+        if (host) CU(cudaMemcpyAsync(d_p + p_off[i], im[i].pixels, im[i].pixels_len, cudaMemcpyHostToDevice, ctx->stream));
+        fd[i].pixels = host ? d_p + p_off[i] : im[i].pixels;
+        fd[i].pixels_len = im[i].pixels_len;
+        fd[i].filtered = d_f + f_off[i];
+        fd[i].filtered_cap = pngb200_filtered_size(im[i].width, im[i].height, im[i].volume, im[i].interlaced);
+        fd[i].width = im[i].width;
+        fd[i].height = im[i].height;
+        fd[i].volume = im[i].volume;
+        fd[i].depth = im[i].depth;
+        fd[i].interlaced = im[i].interlaced;
+    }
+    int rc = pngb200_filter_batch(ctx, fd.data(), count, PNGB200_MEM_DEVICE);
+    if (rc != PNGB200_OK) return rc;
+    std::vector<DeflateJob> jobs(count);
+    for (size_t i = 0; i < count; ++i) {
+        jobs[i].src = fd[i].filtered;
+        jobs[i].n = fd[i].filtered_cap;
+        jobs[i].dst = host ? d_o + o_off[i] : im[i].idat;
+        jobs[i].cap = im[i].idat_cap;
+        jobs[i].format = im[i].format;
+        jobs[i].level = im[i].level;
+        jobs[i].exponent = 15;
+        jobs[i].pad = 0;
+    }
+    std::vector<DeflateResult> res(count);
+    rc = run_deflate(ctx, jobs, res.data());
+    if (rc != PNGB200_OK) return rc;
+    for (size_t i = 0; i < count; ++i) {
+        im[i].status = res[i].status;
+        im[i].checksum = res[i].checksum;
+        im[i].blocks = res[i].blocks;
+        im[i].produced = res[i].produced;
+        if (host && res[i].status == PNGB200_OK)
+            CU(cudaMemcpyAsync(im[i].idat, d_o + o_off[i], res[i].produced, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PNGB200_OK;
+}
+
+extern "C" {
 // ---------------- streaming inflator handle ----------------
 struct pngb200_inflator {
     pngb200_ctx*         ctx;
