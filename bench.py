@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--kind", default="photo", choices=["photo", "graphic", "noise"])
     ap.add_argument("--level", type=int, default=6, help="zlib level of the input streams")
     ap.add_argument("--inflate-mode", type=int, default=0)
+    ap.add_argument("--mode", default="decode", choices=["decode", "encode"])
+    ap.add_argument("--encode-level", type=int, default=9)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: <= 8 GB pinned)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -186,6 +188,9 @@ def main():
                 "e2e": {"value": v, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
+
+    if args.mode == "encode":
+        return main_encode(args, w, h, bpp, depth, rank, local_rank, world, config)
 
     # ---------------- our arm ----------------
     import torch
@@ -362,6 +367,109 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def main_encode(args, w, h, bpp, depth, rank, local_rank, world, config):
+    """BASELINE.json config 3: batch encode (filter select + deflate level 9), MPixels/s."""
+    import torch
+    import torch.distributed as dist
+    import corpus
+    npix, storage_bytes = w * h, w * h * bpp
+    config = dict(config, workload=config["workload"].replace("zlib level %d" % args.level, "encode level %d" % args.encode_level))
+    imgs = [np.ascontiguousarray(corpus.make(args.kind, w, h, i, depth == 16) if args.kind == "photo"
+                                 else corpus.make(args.kind, w, h, i)).tobytes() for i in range(args.unique)]
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle
+        oracle.lib()
+        threads = os.cpu_count() or 1
+        per_step = args.cpu_images or min(threads, 32)
+
+        def one(i):
+            f = oracle.png_filter(imgs[i % len(imgs)], w, h, 8 * bpp, depth)
+            return len(oracle.deflate(f, args.encode_level))
+
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                list(ex.map(one, range(per_step)))
+        dt = time.perf_counter() - t0
+        v = args.steps * per_step * npix / dt / 1e6
+        print(json.dumps({"impl": "reference", "metric": "MPixels/s encode (filter+deflate)", "value": v,
+                          "unit": "MPixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "MPixels/s", "cores": threads, "kind": "port",
+                                           "sample": f"{per_step} images per step over {threads} host threads"},
+                          "e2e": {"value": v, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("swift-png_b200")
+    ctx = pkg.Context(local_rank)
+    L, B = ctx._lib, args.batch
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    cap = L.pngb200_deflate_bound(pkg.filtered_size(w, h, 8 * bpp))
+    d_px = [torch.frombuffer(bytearray(imgs[i % len(imgs)]), dtype=torch.uint8).cuda() for i in range(B)]
+    d_out = torch.empty((B, cap), dtype=torch.uint8, device="cuda")
+    descs = (pkg.EncodeDesc * B)()
+    for i in range(B):
+        descs[i].pixels, descs[i].pixels_len = d_px[i].data_ptr(), storage_bytes
+        descs[i].idat, descs[i].idat_cap = d_out[i].data_ptr(), cap
+        descs[i].width, descs[i].height = w, h
+        descs[i].volume, descs[i].depth, descs[i].level = 8 * bpp, depth, args.encode_level
+
+    def step():
+        ctx.check(L.pngb200_encode_batch(ctx.handle, descs, B, pkg.MEM_DEVICE))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3) if B * npix < 3e8 else 1):
+        step()
+    assert all(descs[i].status == 0 for i in range(B))
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank != 0:
+        return
+    comp = sum(descs[i].produced for i in range(B))
+    # bit-exactness in the same run: image 0's IDAT payload == the CPU restatement's, and it inflates
+    from oracle import oracle
+    mine = bytes(d_out[0, : descs[0].produced].cpu().numpy().tobytes())
+    t0 = time.perf_counter()
+    ref = oracle.deflate(oracle.png_filter(imgs[0], w, h, 8 * bpp, depth), args.encode_level)
+    cpu_dt = time.perf_counter() - t0
+    assert mine == ref, "encode output differs from the oracle"
+    peak, peak_src = peaks()
+    alg = B * storage_bytes + comp
+    value = world * B * npix * args.steps / (ms / 1e3) / 1e6
+    line = {"metric": "MPixels/s encode (filter+deflate)", "value": value, "unit": "MPixels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "clocks": clocks.summary(), "gpu_launches": int(ctx.launches - launches0), "e2e": None,
+            "roofline": {"bound": "hbm", "kernel": "deflate_kernel", "achieved": alg / (ms / args.steps / 1e3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms / args.steps / 1e3) / 1e9 / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
+            "cpu_baseline": {"value": npix / cpu_dt / 1e6, "unit": "MPixels/s", "cores": 1, "kind": "port",
+                             "sample": f"1 image of the same workload on 1 host thread in {cpu_dt:.1f}s (oracle/)"},
+            "bit_exact": True, "compression_ratio": B * storage_bytes / comp}
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":
