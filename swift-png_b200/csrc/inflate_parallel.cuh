@@ -175,27 +175,32 @@ __device__ __forceinline__ uint32_t bit_mask(uint32_t lo, uint32_t hi)  // bits 
 {
     return (hi >= 32 ? ~0u : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
 }
+// spans of <= 33 bits touch at most two words: straight-line fast path, generic loop otherwise
 __device__ __forceinline__ void bits_set(uint32_t* U, uint32_t a, uint32_t b)
 {
-    for (uint32_t w = a >> 5; w <= (b - 1) >> 5; ++w) {
-        uint32_t lo = w == (a >> 5) ? (a & 31) : 0, hi = w == ((b - 1) >> 5) ? ((b - 1) & 31) + 1 : 32;
-        atomicOr(U + w, bit_mask(lo, hi));
-    }
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    if (wa == wb) { atomicOr(U + wa, bit_mask(a & 31, ((b - 1) & 31) + 1)); return; }
+    atomicOr(U + wa, bit_mask(a & 31, 32));
+    for (uint32_t w = wa + 1; w < wb; ++w) atomicOr(U + w, ~0u);
+    atomicOr(U + wb, bit_mask(0, ((b - 1) & 31) + 1));
 }
 __device__ __forceinline__ void bits_clear(uint32_t* U, uint32_t a, uint32_t b)
 {
-    for (uint32_t w = a >> 5; w <= (b - 1) >> 5; ++w) {
-        uint32_t lo = w == (a >> 5) ? (a & 31) : 0, hi = w == ((b - 1) >> 5) ? ((b - 1) & 31) + 1 : 32;
-        atomicAnd(U + w, ~bit_mask(lo, hi));
-    }
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    if (wa == wb) { atomicAnd(U + wa, ~bit_mask(a & 31, ((b - 1) & 31) + 1)); return; }
+    atomicAnd(U + wa, ~bit_mask(a & 31, 32));
+    for (uint32_t w = wa + 1; w < wb; ++w) atomicAnd(U + w, 0u);
+    atomicAnd(U + wb, ~bit_mask(0, ((b - 1) & 31) + 1));
 }
 __device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t a, uint32_t b)
 {
     const volatile uint32_t* V = U;
-    uint32_t any = 0;
-    for (uint32_t w = a >> 5; w <= (b - 1) >> 5; ++w) {
-        uint32_t lo = w == (a >> 5) ? (a & 31) : 0, hi = w == ((b - 1) >> 5) ? ((b - 1) & 31) + 1 : 32;
-        any |= V[w] & bit_mask(lo, hi);
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    uint32_t any;
+    if (wa == wb) any = V[wa] & bit_mask(a & 31, ((b - 1) & 31) + 1);
+    else {
+        any = (V[wa] & bit_mask(a & 31, 32)) | (V[wb] & bit_mask(0, ((b - 1) & 31) + 1));
+        for (uint32_t w = wa + 1; w < wb; ++w) any |= V[w];
     }
     __threadfence_block();
     return any == 0;
@@ -209,6 +214,14 @@ __device__ __forceinline__ void lz_copy(uint8_t* img, const uint8_t* hbm, bool i
 {
     const int64_t src = (int64_t)o - (int64_t)dist;
     uint8_t*      to  = img + o;
+    if (run <= 4 && dist >= 4 && (img_is_hbm || src >= 0 || src + (int64_t)run <= 0)) {
+        // the common short copy: all loads first, then the stores
+        const uint8_t* from = (img_is_hbm || src < 0) ? hbm + src : img + src;
+        uint8_t b0 = from[0], b1 = from[1], b2 = from[2], b3 = run == 4 ? from[3] : 0;
+        to[0] = b0; to[1] = b1; to[2] = b2;
+        if (run == 4) to[3] = b3;
+        return;
+    }
     if (img_is_hbm || src >= 0 || src + (int64_t)run <= 0) {
         const uint8_t* from = (img_is_hbm || src < 0) ? hbm + src : img + src;
         if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
@@ -420,6 +433,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         SmemBits b;
                         b.init(sh.words, my_start);
                         uint32_t o = o_start;
+                        uint32_t mw = o_start >> 5, mbits = 0;   // pending unresolved-bit word
                         while (b.pos < limit) {
                             b.refill();
                             uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, (uint32_t)b.buf);
@@ -438,13 +452,25 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                                     sh.anomaly = 1;
                                     break;
                                 }
-                                bits_set(U, o, o + run);
+                                // flag [o, o + run) as unresolved; words are flushed once, when left
+                                for (uint32_t a = o, e2 = o + run; a < e2;) {
+                                    const uint32_t w = a >> 5;
+                                    if (w != mw) {
+                                        if (mbits) atomicOr(U + mw, mbits);
+                                        mw = w;
+                                        mbits = 0;
+                                    }
+                                    const uint32_t hi = min(e2, (w + 1) << 5);
+                                    mbits |= bit_mask(a & 31, ((hi - 1) & 31) + 1);
+                                    a = hi;
+                                }
                                 list[c_next++] = CopyItem{o, run | (dist - 1) << 16};  // list is sorted by o
                                 o += run;
                             } else {
                                 break;  // end of block
                             }
                         }
+                        if (mbits) atomicOr(U + mw, mbits);
                     }
                     __threadfence_block();
                     __syncthreads();
