@@ -132,6 +132,50 @@ struct SmemBits {
     }
 };
 
+// Block headers are parsed out of a shared-memory copy of the next 768 bytes of the stream (a
+// dynamic header is at most 566 bytes), same interface as BitReader.
+constexpr uint32_t PAR_HDR_WORDS = 192;
+struct StagedReader {
+    const uint32_t* w;
+    uint64_t        base_bit, total_bits, pos;
+    uint32_t        wi;
+    uint64_t        buf;
+    int             cnt;
+    __device__ void init(const uint32_t* words, uint64_t base, uint64_t total, uint64_t p)
+    {
+        w = words; base_bit = base; total_bits = total;
+        seek(p);
+    }
+    __device__ void seek(uint64_t p)
+    {
+        pos = p;
+        wi  = (uint32_t)((p - base_bit) >> 5);
+        buf = 0;
+        cnt = 0;
+        refill();
+        int skip = (int)(p & 31);
+        buf >>= skip;
+        cnt -= skip;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        while (cnt <= 32) {
+            buf |= (uint64_t)(wi < PAR_HDR_WORDS ? w[wi] : 0u) << cnt;
+            cnt += 32;
+            ++wi;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek() const { return (uint32_t)buf; }
+    __device__ __forceinline__ void consume(int n) { buf >>= n; cnt -= n; pos += n; }
+    __device__ __forceinline__ uint32_t take(int n)
+    {
+        uint32_t v = (uint32_t)buf & (n >= 32 ? ~0u : ((1u << n) - 1u));
+        consume(n);
+        return v;
+    }
+    __device__ __forceinline__ bool have(uint64_t n) const { return pos + n <= total_bits; }
+};
+
 // sync-phase decode: symbol boundaries and output byte count only
 __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t start, uint32_t limit,
                                                  uint32_t& exit_bit, uint32_t& nout, uint32_t& ncopy,
@@ -142,30 +186,26 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
     nout  = 0;
     ncopy = 0;
     flags = 0;
+    // literal and copy tokens run through ONE predicated body: in a warp some lanes always hold a
+    // literal while others hold a copy, so two divergent paths would cost their sum every iteration
     while (b.pos < limit) {
         b.refill();
-        uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, (uint32_t)b.buf);
-        uint32_t kind = e_kind(e);
-        if (kind == K_LIT) {
-            b.consume(e_len(e));
-            ++nout;
-        } else if (kind == K_BASE) {
-            b.consume(e_len(e));
-            uint32_t run = e_value(e) + b.take(e_extra(e));
-            b.refill();
-            uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, (uint32_t)b.buf);
-            if (e_kind(d) != K_BASE) { flags = PF_BAD; break; }
-            b.consume(e_len(d) + e_extra(d));
-            nout += run;
-            ++ncopy;
-        } else if (kind == K_EOB) {
-            b.consume(e_len(e));
-            flags = PF_EOB;
-            break;
-        } else {
-            flags = PF_BAD;
+        const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, (uint32_t)b.buf);
+        const uint32_t kind = e_kind(e);
+        if (kind >= K_EOB) {  // end of block, or an invalid code: rare, leave the loop
+            if (kind == K_EOB) { b.consume(e_len(e)); flags = PF_EOB; }
+            else flags = PF_BAD;
             break;
         }
+        const bool is_copy = kind == K_BASE;
+        b.consume(e_len(e));
+        const uint32_t run = e_value(e) + b.take(is_copy ? e_extra(e) : 0u);
+        b.refill();
+        const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, (uint32_t)b.buf);  // ignored for literals
+        if (is_copy && e_kind(d) != K_BASE) { flags = PF_BAD; break; }
+        b.consume(is_copy ? e_len(d) + e_extra(d) : 0u);
+        nout += is_copy ? run : 1u;
+        ncopy += is_copy ? 1u : 0u;
     }
     exit_bit = (flags & PF_BAD) ? max(b.pos, limit) : b.pos;
 }
@@ -293,11 +333,18 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
         while (st == PNGB200_OK && phase == 1) {
             // warp 0 walks the header bits alone; the CTA then builds the tables together
             __syncthreads();
-            if (warp == 0) {
-                int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
-                uint32_t stored0 = 0;
-                int st0 = parse_block_header(br, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
-                if (lane == 0) sh.hdr = ParHeader{st0, type0, final0, nlit0, ndist0, stored0, br.pos};
+            {
+                const uint64_t hbase = br.pos >> 5;
+                for (uint32_t k = t; k < PAR_HDR_WORDS; k += PAR_THREADS) sh.words[k] = br.load_word(hbase + k);
+                __syncthreads();
+                if (warp == 0) {
+                    int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
+                    uint32_t stored0 = 0;
+                    StagedReader sr;
+                    sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
+                    int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
+                    if (lane == 0) sh.hdr = ParHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                }
             }
             __syncthreads();
             const ParHeader hdr = sh.hdr;
@@ -305,7 +352,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
             if (st != PNGB200_OK) break;
             const int      type = hdr.type, final = hdr.final;
             const uint32_t stored = hdr.stored;
-            if (warp != 0) br.seek(hdr.pos);
+            br.seek(hdr.pos);
             if (type != 0) {
                 st = build_block_tables(&sh.ser, r, hdr.nlit, hdr.ndist, (int)t, PAR_THREADS);
                 if (st != PNGB200_OK) break;
@@ -436,39 +483,38 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         uint32_t mw = o_start >> 5, mbits = 0;   // pending unresolved-bit word
                         while (b.pos < limit) {
                             b.refill();
-                            uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, (uint32_t)b.buf);
-                            uint32_t kind = e_kind(e);
-                            if (kind == K_LIT) {
-                                b.consume(e_len(e));
-                                img[o++] = (uint8_t)e_value(e);
-                            } else if (kind == K_BASE) {
-                                b.consume(e_len(e));
-                                uint32_t run = e_value(e) + b.take(e_extra(e));
-                                b.refill();
-                                uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, (uint32_t)b.buf);
-                                b.consume(e_len(d));
-                                uint32_t dist = e_value(d) + b.take(e_extra(d));
-                                if ((uint64_t)dist > out + o) {  // invalidStringReference
-                                    sh.anomaly = 1;
-                                    break;
-                                }
-                                // flag [o, o + run) as unresolved; words are flushed once, when left
-                                for (uint32_t a = o, e2 = o + run; a < e2;) {
-                                    const uint32_t w = a >> 5;
-                                    if (w != mw) {
-                                        if (mbits) atomicOr(U + mw, mbits);
-                                        mw = w;
-                                        mbits = 0;
-                                    }
-                                    const uint32_t hi = min(e2, (w + 1) << 5);
-                                    mbits |= bit_mask(a & 31, ((hi - 1) & 31) + 1);
-                                    a = hi;
-                                }
-                                list[c_next++] = CopyItem{o, run | (dist - 1) << 16};  // list is sorted by o
-                                o += run;
-                            } else {
-                                break;  // end of block
+                            const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, (uint32_t)b.buf);
+                            const uint32_t kind = e_kind(e);
+                            if (kind >= K_EOB) break;  // end of block
+                            const bool is_copy = kind == K_BASE;
+                            b.consume(e_len(e));
+                            const uint32_t run = e_value(e) + b.take(is_copy ? e_extra(e) : 0u);
+                            b.refill();
+                            const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, (uint32_t)b.buf);
+                            b.consume(is_copy ? e_len(d) : 0u);
+                            const uint32_t dist = e_value(d) + b.take(is_copy ? e_extra(d) : 0u);
+                            if (!is_copy) {
+                                img[o++] = (uint8_t)run;  // e_value of a literal entry is the byte
+                                continue;
                             }
+                            if ((uint64_t)dist > out + o) {  // invalidStringReference
+                                sh.anomaly = 1;
+                                break;
+                            }
+                            // flag [o, o + run) as unresolved; words are flushed once, when left
+                            for (uint32_t a = o, e2 = o + run; a < e2;) {
+                                const uint32_t w = a >> 5;
+                                if (w != mw) {
+                                    if (mbits) atomicOr(U + mw, mbits);
+                                    mw = w;
+                                    mbits = 0;
+                                }
+                                const uint32_t hi = min(e2, (w + 1) << 5);
+                                mbits |= bit_mask(a & 31, ((hi - 1) & 31) + 1);
+                                a = hi;
+                            }
+                            list[c_next++] = CopyItem{o, run | (dist - 1) << 16};  // list is sorted by o
+                            o += run;
                         }
                         if (mbits) atomicOr(U + mw, mbits);
                     }

@@ -153,8 +153,8 @@ __device__ int read_stream_header(BitReader& br, int format, StreamResult* r)
 // of a fixed/dynamic block written to sh->lens (literal/length codes first, then distance codes).
 // Returns PNGB200_OK with *type/*final/*stored_len/*nlit/*ndist set, PNGB200_NEED_MORE_INPUT, or
 // an error.  Stream.readBlockMetadata / readBlockTables (LZ77.InflatorBuffers.Stream.swift:59-263).
-template <typename Shared>
-__device__ int parse_block_header(BitReader& br, Shared* sh, StreamResult* r, int lane, int* type, int* final,
+template <typename Reader, typename Shared>
+__device__ int parse_block_header(Reader& br, Shared* sh, StreamResult* r, int lane, int* type, int* final,
                                   uint32_t* stored_len, int* nlit_out, int* ndist_out)
 {
     if (!br.have(3)) return PNGB200_NEED_MORE_INPUT;
