@@ -132,6 +132,39 @@ struct SmemBits {
     }
 };
 
+// Bit reader of the decode passes: two 32-bit words of look-ahead in registers, one funnel shift
+// per peek (>= 32 valid bits: a literal/length code + extra needs <= 20, a distance code + extra
+// <= 28), at most one predicated shared-memory load per skip.  ~15 instructions per literal.
+struct FastBits {
+    const uint32_t* w;
+    uint32_t        wi;        // next word to fetch
+    uint32_t        cur, nxt;
+    uint32_t        off;       // < 32 at every peek
+    uint32_t        pos;
+    __device__ __forceinline__ void init(const uint32_t* words, uint32_t start)
+    {
+        w = words;
+        const uint32_t W = start >> 5;
+        cur = w[W + (W >> 3)];
+        nxt = w[W + 1 + ((W + 1) >> 3)];
+        wi  = W + 2;
+        off = start & 31;
+        pos = start;
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, off); }
+    __device__ __forceinline__ void skip(uint32_t n)  // n <= 32
+    {
+        off += n;
+        pos += n;
+        if (off >= 32) {
+            cur = nxt;
+            nxt = w[wi + (wi >> 3)];
+            ++wi;
+            off -= 32;
+        }
+    }
+};
+
 // Block headers are parsed out of a shared-memory copy of the next 768 bytes of the stream (a
 // dynamic header is at most 566 bytes), same interface as BitReader.
 constexpr uint32_t PAR_HDR_WORDS = 192;
@@ -181,7 +214,7 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
                                                  uint32_t& exit_bit, uint32_t& nout, uint32_t& ncopy,
                                                  uint32_t& flags)
 {
-    SmemBits b;
+    FastBits b;
     b.init(sh.words, start);
     nout  = 0;
     ncopy = 0;
@@ -189,21 +222,21 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
     // literal and copy tokens run through ONE predicated body: in a warp some lanes always hold a
     // literal while others hold a copy, so two divergent paths would cost their sum every iteration
     while (b.pos < limit) {
-        b.refill();
-        const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, (uint32_t)b.buf);
+        const uint32_t bits = b.peek();
+        const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, bits);
         const uint32_t kind = e_kind(e);
         if (kind >= K_EOB) {  // end of block, or an invalid code: rare, leave the loop
-            if (kind == K_EOB) { b.consume(e_len(e)); flags = PF_EOB; }
+            if (kind == K_EOB) { b.skip(e_len(e)); flags = PF_EOB; }
             else flags = PF_BAD;
             break;
         }
-        const bool is_copy = kind == K_BASE;
-        b.consume(e_len(e));
-        const uint32_t run = e_value(e) + b.take(is_copy ? e_extra(e) : 0u);
-        b.refill();
-        const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, (uint32_t)b.buf);  // ignored for literals
+        const bool     is_copy = kind == K_BASE;
+        const uint32_t len = e_len(e), extra = is_copy ? e_extra(e) : 0u;
+        const uint32_t run = e_value(e) + ((bits >> len) & ((1u << extra) - 1u));
+        b.skip(len + extra);
+        const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, b.peek());  // ignored for literals
         if (is_copy && e_kind(d) != K_BASE) { flags = PF_BAD; break; }
-        b.consume(is_copy ? e_len(d) + e_extra(d) : 0u);
+        b.skip(is_copy ? e_len(d) + e_extra(d) : 0u);
         nout += is_copy ? run : 1u;
         ncopy += is_copy ? 1u : 0u;
     }
@@ -477,22 +510,24 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     uint8_t* const  img    = in_hbm ? wdst : sh.outbuf + shift;
                     uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
                     if (t < nvalid) {
-                        SmemBits b;
+                        FastBits b;
                         b.init(sh.words, my_start);
                         uint32_t o = o_start;
                         uint32_t mw = o_start >> 5, mbits = 0;   // pending unresolved-bit word
                         while (b.pos < limit) {
-                            b.refill();
-                            const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, (uint32_t)b.buf);
+                            const uint32_t bits = b.peek();
+                            const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, bits);
                             const uint32_t kind = e_kind(e);
                             if (kind >= K_EOB) break;  // end of block
-                            const bool is_copy = kind == K_BASE;
-                            b.consume(e_len(e));
-                            const uint32_t run = e_value(e) + b.take(is_copy ? e_extra(e) : 0u);
-                            b.refill();
-                            const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, (uint32_t)b.buf);
-                            b.consume(is_copy ? e_len(d) : 0u);
-                            const uint32_t dist = e_value(d) + b.take(is_copy ? e_extra(d) : 0u);
+                            const bool     is_copy = kind == K_BASE;
+                            const uint32_t len = e_len(e), extra = is_copy ? e_extra(e) : 0u;
+                            const uint32_t run = e_value(e) + ((bits >> len) & ((1u << extra) - 1u));
+                            b.skip(len + extra);
+                            const uint32_t dbits = b.peek();
+                            const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, dbits);
+                            const uint32_t dlen = e_len(d), dextra = e_extra(d);
+                            const uint32_t dist = e_value(d) + ((dbits >> dlen) & ((1u << dextra) - 1u));
+                            b.skip(is_copy ? dlen + dextra : 0u);
                             if (!is_copy) {
                                 img[o++] = (uint8_t)run;  // e_value of a literal entry is the byte
                                 continue;
