@@ -32,7 +32,7 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (width, height, sixteen, default batch per GPU, default unique images)
-    "8k-rgba8": (7680, 4320, False, 296, 2),
+    "8k-rgba8": (7680, 4320, False, 444, 2),
     "1080p-rgba8": (1920, 1080, False, 1024, 16),
     "8k-rgba16": (7680, 4320, True, 8, 2),
     "small": (512, 512, False, 64, 4),

@@ -22,7 +22,7 @@ from dataclasses import dataclass
 from . import shard  # noqa: F401  (multi-GPU partitioning helpers)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpngb200.so")
+LIB_PATH = os.environ.get("PNGB200_LIB") or os.path.join(_HERE, "libpngb200.so")  # override: tuning experiments only
 HEADER_PATH = os.path.join(_HERE, "..", "include", "pngb200.h")
 
 # pngb200_status

@@ -1,11 +1,11 @@
-// inflate_parallel.cuh -- intra-stream parallel DEFLATE inflate: one CTA (512 threads) per stream,
-// two CTAs resident per SM so that one stream's serial stretches (header parse, fix-up rounds)
-// hide behind the other's parallel ones.
+// inflate_parallel.cuh -- intra-stream parallel DEFLATE inflate: one CTA (256 threads) per stream,
+// four CTAs resident per SM so that one stream's serial stretches (header parse, fix-up rounds)
+// hide behind the others' parallel ones.
 //
 // DEFLATE has no sync markers, but Huffman codes self-synchronise: a decoder started at a wrong
 // bit offset falls into step with the true symbol sequence after a few symbols.  Per block warp 0
 // parses the header, the CTA builds the decode tables (shared memory), then the block is eaten in
-// WAVES of 512 subsequences x 256 bits (16 KiB of compressed data staged in shared memory, padded
+// WAVES of 256 subsequences x 256 bits (8 KiB of compressed data staged in shared memory, padded
 // 9/8 so that lane-strided word reads are bank-conflict free):
 //
 //   1. sync    every thread decodes its subsequence from a guessed start (thread 0's start is
@@ -16,7 +16,7 @@
 //              chain ends the wave (and the block).
 //   2. scan    a CTA-wide exclusive scan of per-subsequence output byte counts.
 //   3. emit    every thread decodes its subsequence once more; literals are written into a
-//              shared-memory image of the wave's output (32 KiB; HBM directly if the wave expands
+//              shared-memory image of the wave's output (16 KiB; HBM directly if the wave expands
 //              to more), every LZ77 copy becomes an item on a CTA-wide work list and its
 //              destination bytes are flagged in an "unresolved" bitmap (1 bit per output byte).
 //   4. resolve warps sweep the work list without CTA barriers: a copy runs as soon as none of its
@@ -40,14 +40,21 @@
 
 namespace pngb200 {
 
-constexpr int      PAR_THREADS      = 512;
-constexpr int      PAR_CTAS_PER_SM  = 2;
+// CTA shape (tunable at compile time; measured r01: 512x2 171.9 ms, 384x3 142.7, 256x4 131.2,
+// 128x8 123.2 ms on 1184 x 1080p -- more, smaller CTAs hide each other's barrier phases)
+#ifndef PAR_T
+#define PAR_T 256
+#define PAR_C 4
+#define PAR_O 16384
+#endif
+constexpr int      PAR_THREADS      = PAR_T;
+constexpr int      PAR_CTAS_PER_SM  = PAR_C;
 constexpr int      PAR_WARPS        = PAR_THREADS / 32;
 constexpr uint32_t PAR_SUB_BITS     = 256;
 constexpr uint32_t PAR_SUB_WORDS    = PAR_SUB_BITS / 32;
 constexpr uint32_t PAR_WAVE_WORDS   = PAR_THREADS * PAR_SUB_WORDS + 8;
 constexpr uint32_t PAR_SMEM_WORDS   = PAR_WAVE_WORDS + PAR_WAVE_WORDS / 8 + 1;
-constexpr uint32_t PAR_OUT_BYTES    = 32768;                         // wave output image in smem
+constexpr uint32_t PAR_OUT_BYTES    = PAR_O;                         // wave output image in smem
 constexpr uint32_t PAR_BITMAP_WORDS = PAR_OUT_BYTES / 32;
 constexpr uint32_t PAR_LIST_CAP     = PAR_THREADS * (PAR_SUB_BITS / 2);  // >= copies per wave (2 bits min each)
 constexpr uint64_t PAR_MAX_WAVE_OUT = (uint64_t)PAR_LIST_CAP * 258;
