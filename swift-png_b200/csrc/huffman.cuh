@@ -13,15 +13,29 @@
 
 namespace pngb200 {
 
-// entry: [3:0] code length, [7:4] extra bits (or subtable bits), [10:8] kind, [31:16] value
+// entry: [3:0] code length, [8:4] bits to skip (code length + extra bits; root + subtable bits for a
+// pointer), [9] copy (length / distance base), [10] special, [12:11] special kind (0 end of block,
+// 1 subtable pointer, 2 invalid), [31:16] value.  Laid out so that the decode loops test single bits
+// and pull the extra-bit field with one BFE (width skip - length, 0 for literals).
 enum : uint32_t { K_LIT = 0, K_BASE = 1, K_EOB = 2, K_PTR = 3, K_INVALID = 4 };
+enum : uint32_t { E_COPY = 1u << 9, E_SPECIAL = 1u << 10, E_PTR = 1u << 11, E_INVALID = 2u << 11 };
 __device__ __forceinline__ uint32_t mk_entry(uint32_t kind, uint32_t len, uint32_t extra, uint32_t value)
 {
-    return len | extra << 4 | kind << 8 | value << 16;
+    uint32_t e = len | (len + extra) << 4 | value << 16;
+    if (kind == K_BASE) e |= E_COPY;
+    else if (kind == K_EOB) e |= E_SPECIAL;
+    else if (kind == K_PTR) e |= E_SPECIAL | E_PTR;
+    else if (kind == K_INVALID) e |= E_SPECIAL | E_INVALID;
+    return e;
 }
 __device__ __forceinline__ uint32_t e_len(uint32_t e) { return e & 15u; }
-__device__ __forceinline__ uint32_t e_extra(uint32_t e) { return (e >> 4) & 15u; }
-__device__ __forceinline__ uint32_t e_kind(uint32_t e) { return (e >> 8) & 7u; }
+__device__ __forceinline__ uint32_t e_skip(uint32_t e) { return (e >> 4) & 31u; }
+__device__ __forceinline__ uint32_t e_extra(uint32_t e) { return e_skip(e) - e_len(e); }
+__device__ __forceinline__ uint32_t e_kind(uint32_t e)
+{
+    return (e & E_SPECIAL) ? (((e >> 11) & 3u) == 0 ? K_EOB : ((e >> 11) & 3u) == 1 ? K_PTR : K_INVALID)
+                           : ((e >> 9) & 1u);
+}
 __device__ __forceinline__ uint32_t e_value(uint32_t e) { return e >> 16; }
 
 constexpr int LIT_ROOT  = 10;

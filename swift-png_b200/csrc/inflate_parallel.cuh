@@ -142,18 +142,32 @@ struct SmemBits {
 // Bit reader of the decode passes: two 32-bit words of look-ahead in registers, one funnel shift
 // per peek (>= 32 valid bits: a literal/length code + extra needs <= 20, a distance code + extra
 // <= 28), at most one predicated shared-memory load per skip.  ~15 instructions per literal.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
+{
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pos), "r"(len));
+    return r;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 struct FastBits {
-    const uint32_t* w;
-    uint32_t        wi;        // next word to fetch
-    uint32_t        cur, nxt;
-    uint32_t        off;       // < 32 at every peek
-    uint32_t        pos;
-    __device__ __forceinline__ void init(const uint32_t* words, uint32_t start)
+    uint32_t wbase;     // shared-memory address of the staged words
+    uint32_t wi;        // next word to fetch
+    uint32_t cur, nxt;
+    uint32_t off;       // < 32 at every peek
+    uint32_t pos;
+    __device__ __forceinline__ void init(uint32_t words_addr, uint32_t start)
     {
-        w = words;
+        wbase = words_addr;
         const uint32_t W = start >> 5;
-        cur = w[W + (W >> 3)];
-        nxt = w[W + 1 + ((W + 1) >> 3)];
+        cur = lds32(wbase + ((W + (W >> 3)) << 2));
+        nxt = lds32(wbase + ((W + 1 + ((W + 1) >> 3)) << 2));
         wi  = W + 2;
         off = start & 31;
         pos = start;
@@ -165,12 +179,22 @@ struct FastBits {
         pos += n;
         if (off >= 32) {
             cur = nxt;
-            nxt = w[wi + (wi >> 3)];
+            nxt = lds32(wbase + ((wi + (wi >> 3)) << 2));
             ++wi;
             off -= 32;
         }
     }
 };
+
+// one table lookup of the decode passes: root entry, subtable entry behind a pointer (rare)
+template <int ROOT>
+__device__ __forceinline__ uint32_t fast_lookup(uint32_t table_addr, uint32_t bits)
+{
+    uint32_t e = lds32(table_addr + ((bits & ((1u << ROOT) - 1u)) << 2));
+    if ((e & (E_SPECIAL | E_PTR | E_INVALID)) == (E_SPECIAL | E_PTR))
+        e = lds32(table_addr + (((e >> 16) + bfe32(bits, ROOT, e_skip(e) - ROOT)) << 2));
+    return e;
+}
 
 // Block headers are parsed out of a shared-memory copy of the next 768 bytes of the stream (a
 // dynamic header is at most 566 bytes), same interface as BitReader.
@@ -222,7 +246,8 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
                                                  uint32_t& flags)
 {
     FastBits b;
-    b.init(sh.words, start);
+    b.init(smem_addr(sh.words), start);
+    const uint32_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
     nout  = 0;
     ncopy = 0;
     flags = 0;
@@ -230,22 +255,21 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
     // literal while others hold a copy, so two divergent paths would cost their sum every iteration
     while (b.pos < limit) {
         const uint32_t bits = b.peek();
-        const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, bits);
-        const uint32_t kind = e_kind(e);
-        if (kind >= K_EOB) {  // end of block, or an invalid code: rare, leave the loop
-            if (kind == K_EOB) { b.skip(e_len(e)); flags = PF_EOB; }
-            else flags = PF_BAD;
+        const uint32_t e = fast_lookup<LIT_ROOT>(lit, bits);
+        if (e & E_SPECIAL) {  // end of block, or an invalid code: rare, leave the loop
+            if (e & E_INVALID) flags = PF_BAD;
+            else { b.skip(e_len(e)); flags = PF_EOB; }
             break;
         }
-        const bool     is_copy = kind == K_BASE;
-        const uint32_t len = e_len(e), extra = is_copy ? e_extra(e) : 0u;
-        const uint32_t run = e_value(e) + ((bits >> len) & ((1u << extra) - 1u));
-        b.skip(len + extra);
-        const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, b.peek());  // ignored for literals
-        if (is_copy && e_kind(d) != K_BASE) { flags = PF_BAD; break; }
-        b.skip(is_copy ? e_len(d) + e_extra(d) : 0u);
-        nout += is_copy ? run : 1u;
-        ncopy += is_copy ? 1u : 0u;
+        const uint32_t len = e & 15u, skipn = (e >> 4) & 31u;
+        const uint32_t run = (e >> 16) + bfe32(bits, len, skipn - len);  // literals: width 0
+        b.skip(skipn);
+        const uint32_t copy = e & E_COPY;
+        const uint32_t d = fast_lookup<DIST_ROOT>(dst, b.peek());  // ignored for literals
+        if (copy && (d & E_SPECIAL)) { flags = PF_BAD; break; }
+        b.skip(copy ? (d >> 4) & 31u : 0u);
+        nout += copy ? run : 1u;
+        ncopy += copy >> 9;
     }
     exit_bit = (flags & PF_BAD) ? max(b.pos, limit) : b.pos;
 }
@@ -518,23 +542,23 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
                     if (t < nvalid) {
                         FastBits b;
-                        b.init(sh.words, my_start);
+                        b.init(smem_addr(sh.words), my_start);
+                        const uint32_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
                         uint32_t o = o_start;
                         uint32_t mw = o_start >> 5, mbits = 0;   // pending unresolved-bit word
                         while (b.pos < limit) {
                             const uint32_t bits = b.peek();
-                            const uint32_t e = lookup<LIT_ROOT>(sh.ser.lit, bits);
-                            const uint32_t kind = e_kind(e);
-                            if (kind >= K_EOB) break;  // end of block
-                            const bool     is_copy = kind == K_BASE;
-                            const uint32_t len = e_len(e), extra = is_copy ? e_extra(e) : 0u;
-                            const uint32_t run = e_value(e) + ((bits >> len) & ((1u << extra) - 1u));
-                            b.skip(len + extra);
+                            const uint32_t e = fast_lookup<LIT_ROOT>(lit, bits);
+                            if (e & E_SPECIAL) break;  // end of block
+                            const uint32_t len = e & 15u, skipn = (e >> 4) & 31u;
+                            const uint32_t run = (e >> 16) + bfe32(bits, len, skipn - len);
+                            b.skip(skipn);
+                            const bool     is_copy = (e & E_COPY) != 0;
                             const uint32_t dbits = b.peek();
-                            const uint32_t d = lookup<DIST_ROOT>(sh.ser.dist, dbits);
-                            const uint32_t dlen = e_len(d), dextra = e_extra(d);
-                            const uint32_t dist = e_value(d) + ((dbits >> dlen) & ((1u << dextra) - 1u));
-                            b.skip(is_copy ? dlen + dextra : 0u);
+                            const uint32_t d = fast_lookup<DIST_ROOT>(dst, dbits);
+                            const uint32_t dlen = d & 15u, dskip = (d >> 4) & 31u;
+                            const uint32_t dist = (d >> 16) + bfe32(dbits, dlen, dskip - dlen);
+                            b.skip(is_copy ? dskip : 0u);
                             if (!is_copy) {
                                 img[o++] = (uint8_t)run;  // e_value of a literal entry is the byte
                                 continue;
