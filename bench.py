@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--unique", type=int, default=0, help="distinct images (0 = workload default)")
     ap.add_argument("--kind", default="photo", choices=["photo", "graphic", "noise"])
     ap.add_argument("--level", type=int, default=6, help="zlib level of the input streams")
+    ap.add_argument("--encoder", default="zlib", choices=["zlib", "ref"],
+                    help="who compresses the synthetic inputs: zlib (libpng-like streams, default) or 'ref' = "
+                         "our GPU encoder at --encode-level, bit-identical to the reference's own output "
+                         "(slow for 8K: one warp per stream)")
     ap.add_argument("--inflate-mode", type=int, default=0)
     ap.add_argument("--mode", default="decode", choices=["decode", "encode"])
     ap.add_argument("--encode-level", type=int, default=9)
@@ -77,8 +81,14 @@ def make_corpus(args, pkg, ctx):
         else:
             from oracle import oracle
             filtered = oracle.png_filter(storage, w, h, 8 * bpp, 16 if sixteen else 8)
-        comp = zlib.compress(filtered, args.level)
-        out.append(dict(pixels=storage, adler=zlib.adler32(filtered), idat=comp, filtered_len=len(filtered)))
+        comp = zlib.compress(filtered, args.level) if args.encoder == "zlib" or ctx is None else None
+        out.append(dict(pixels=storage, adler=zlib.adler32(filtered), idat=comp, filtered_len=len(filtered),
+                        filtered=filtered if comp is None else None))
+    if ctx is not None and args.encoder == "ref":
+        got = pkg.deflate_batch(ctx, [it["filtered"] for it in out], args.encode_level)
+        for it, (st, comp) in zip(out, got):
+            assert st == 0
+            it["idat"], it["filtered"] = comp, None
     return out
 
 
@@ -158,7 +168,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": f"{args.batch}x {w}x{h} RGBA{depth} per GPU ({args.kind}, zlib level {args.level}, "
+    enc = f"zlib level {args.level}" if args.encoder == "zlib" else f"reference-exact encoder level {args.encode_level}"
+    config = {"workload": f"{args.batch}x {w}x{h} RGBA{depth} per GPU ({args.kind}, {enc}, "
                           f"reference filter rule; {args.unique} distinct images)",
               "images_per_gpu": args.batch, "l2": "inputs larger than L2 (no flush needed)"}
 
@@ -371,11 +382,12 @@ def main():
 
 def main_encode(args, w, h, bpp, depth, rank, local_rank, world, config):
     """BASELINE.json config 3: batch encode (filter select + deflate level 9), MPixels/s."""
+    enc = f"zlib level {args.level}" if args.encoder == "zlib" else f"reference-exact encoder level {args.encode_level}"
     import torch
     import torch.distributed as dist
     import corpus
     npix, storage_bytes = w * h, w * h * bpp
-    config = dict(config, workload=config["workload"].replace("zlib level %d" % args.level, "encode level %d" % args.encode_level))
+    config = dict(config, workload=config["workload"].replace(enc, "encode level %d" % args.encode_level))
     imgs = [np.ascontiguousarray(corpus.make(args.kind, w, h, i, depth == 16) if args.kind == "photo"
                                  else corpus.make(args.kind, w, h, i)).tobytes() for i in range(args.unique)]
     if args.impl == "reference":

@@ -261,3 +261,28 @@ def test_streaming_inflator(pngb200, ctx, orc):
         z.push(bytes(bad))
     assert e.value.status == pngb200.ERR_STREAM_CHECKSUM and e.value.payload[1] == zlib.adler32(data)
     z.close()
+
+
+def test_decode_reference_encoded_streams_large_blocks(pngb200, ctx, orc):
+    """streams exactly as the reference's encoder emits them (level 9: dynamic blocks of 2047, 4095,
+    ... bytes; level 4: <= 2047 terms per block) produced by our bit-exact GPU encoder, decoded by
+    the block-parallel kernel: multi-wave blocks, waves without an end-of-block symbol"""
+    jobs, want = [], []
+    for kind, w, h, level in [("photo", 640, 480, 9), ("graphic", 800, 600, 9), ("photo", 512, 512, 4),
+                              ("noise", 256, 256, 9)]:
+        img = corpus.make(kind, w, h, 7)
+        (st, idat), = pngb200.encode_batch(ctx, [dict(pixels=img.tobytes(), width=w, height=h, volume=32, depth=8)],
+                                           level=level)
+        assert st == 0
+        filtered = orc.png_filter(img.tobytes(), w, h, 32, 8)
+        assert idat == orc.deflate(filtered, level)
+        jobs.append(dict(idat=idat, width=w, height=h, volume=32, depth=8))
+        want.append(img.tobytes())
+    for mode in (1, 2):
+        ctx.set_inflate_mode(mode)
+        try:
+            got = pngb200.decode_batch(ctx, jobs)
+        finally:
+            ctx.set_inflate_mode(0)
+        for g, ref in zip(got, want):
+            assert g.status == 0 and g.pixels == ref
