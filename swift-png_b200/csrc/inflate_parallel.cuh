@@ -40,8 +40,9 @@
 
 namespace pngb200 {
 
-// CTA shape (tunable at compile time; measured r01: 512x2 171.9 ms, 384x3 142.7, 256x4 131.2,
-// 128x8 123.2 ms on 1184 x 1080p -- more, smaller CTAs hide each other's barrier phases)
+// CTA shape (tunable at compile time; measured r01 on 1184 x 1080p: 512x2 171.9 ms, 384x3 142.7,
+// 256x4 131.2, 128x8 123.2 ms -- more, smaller CTAs hide each other's barrier phases; subsequences of
+// 128 / 256 / 512 bits: 160.7 / 127.8 / 157.7 ms)
 #ifndef PAR_T
 #define PAR_T 256
 #define PAR_C 4
@@ -50,7 +51,10 @@ namespace pngb200 {
 constexpr int      PAR_THREADS      = PAR_T;
 constexpr int      PAR_CTAS_PER_SM  = PAR_C;
 constexpr int      PAR_WARPS        = PAR_THREADS / 32;
-constexpr uint32_t PAR_SUB_BITS     = 256;
+#ifndef PAR_S
+#define PAR_S 256
+#endif
+constexpr uint32_t PAR_SUB_BITS     = PAR_S;
 constexpr uint32_t PAR_SUB_WORDS    = PAR_SUB_BITS / 32;
 constexpr uint32_t PAR_WAVE_WORDS   = PAR_THREADS * PAR_SUB_WORDS + 8;
 constexpr uint32_t PAR_SMEM_WORDS   = PAR_WAVE_WORDS + PAR_WAVE_WORDS / 8 + 1;
@@ -97,51 +101,6 @@ struct ParParams {
 
 struct CopyItem { uint32_t o; uint32_t run_dist; };  // run | (dist - 1) << 16
 
-struct SmemBits {
-    const uint32_t* w;
-    uint32_t        wi;
-    uint64_t        buf;
-    int             cnt;
-    uint32_t        pos;
-    __device__ __forceinline__ void init(const uint32_t* words, uint32_t start)
-    {
-        w   = words;
-        wi  = start >> 5;
-        buf = 0;
-        cnt = 0;
-        pos = start;
-        refill();
-        refill();
-        int skip = (int)(start & 31);
-        buf >>= skip;
-        cnt -= skip;
-    }
-    // one word is always enough: a token takes <= 20 bits before the next refill and <= 28 after
-    __device__ __forceinline__ void refill()
-    {
-        if (cnt <= 32) {
-            buf |= (uint64_t)w[wi + (wi >> 3)] << cnt;
-            cnt += 32;
-            ++wi;
-        }
-    }
-    __device__ __forceinline__ void consume(uint32_t n)
-    {
-        buf >>= n;
-        cnt -= (int)n;
-        pos += n;
-    }
-    __device__ __forceinline__ uint32_t take(uint32_t n)
-    {
-        uint32_t v = (uint32_t)buf & ((1u << n) - 1u);
-        consume(n);
-        return v;
-    }
-};
-
-// Bit reader of the decode passes: two 32-bit words of look-ahead in registers, one funnel shift
-// per peek (>= 32 valid bits: a literal/length code + extra needs <= 20, a distance code + extra
-// <= 28), at most one predicated shared-memory load per skip.  ~15 instructions per literal.
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
     uint32_t v;
