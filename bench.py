@@ -352,7 +352,9 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload)
+        entry = json.load(open(tpath)).get(args.workload)
+        if entry and entry.get("batch") == B and args.encoder == "zlib" and args.kind == "photo":
+            traffic = entry["bytes_per_launch"]  # measured once under ncu for exactly this launch shape
     roofline = {"bound": "hbm", "kernel": names[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
