@@ -276,7 +276,7 @@ struct DfState {
     int64_t  n, mask, end_index, dequeued;
     int32_t *head, *prevh, *next;
     uint32_t* graph;   // 32 x u32 per vertex: upstream, depth(unused on device), 30 edges
-    int64_t  limit, capacity, count;
+    int64_t  limit, capacity, count, skip_until;
     int      mode, goal, iterations, generic;
     long     attempts;
 };
@@ -411,26 +411,88 @@ __device__ bool df_compress(DfState& z, DfShared& S)
             }
         }
     } else {
+        // Full mode, 32 positions per step (lane = position).  Every position becomes a vertex and
+        // enters the dictionary whatever the parse does, and its candidate chain is a pure function
+        // of the dictionary state at that position, so a batch does: (D) all 32 dictionary look-ups
+        // against the pre-batch state in parallel, in-batch predecessors by warp match, one batched
+        // update; (M) 32 independent chain walks; (S) the order-dependent skip rule over the lanes.
+        uint32_t* g = z.graph;
         while (df_input_count(z) > 0) {
-            if (df_unfilled(z) <= 0) return true;
-            int64_t a = df_window_update(z, &next);
-            int64_t index = z.count;
-            df_store_vertex(z, df_literal(z, a));
-            int extent = 1;
-            uint32_t* edges = z.graph + (index << 5) + 2;
-            df_window_match(z, a, next, [&](int run, int dist) {
-                if (run > extent) extent = run;
-                uint32_t dd = df_dist_decade((uint32_t)dist);
-                uint32_t cur = edges[dd];   // first wins ties (DeflatorMatches.set(edge:at:))
-                __syncwarp();
-                if ((uint32_t)run > (cur & 0xffffu) && lane == 0) edges[dd] = (uint32_t)dist << 16 | (uint32_t)run;
-                __syncwarp();
-            });
-            int64_t skip = extent - 100 < df_unfilled(z) ? extent - 100 : df_unfilled(z);
-            for (int64_t k = 0; k < skip; ++k) {
-                int64_t b = df_window_update(z, nullptr);
-                df_store_vertex(z, df_literal(z, b));
+            const int64_t unf = df_unfilled(z);
+            if (unf <= 0) return true;
+            const int64_t a0 = z.end_index, left = df_input_count(z);
+            const int     nb = (int)(unf < 32 ? (unf < left ? unf : left) : (left < 32 ? left : 32));
+            const bool    act = (int)lane < nb;
+            const int64_t a = a0 + lane;
+            // ---- (D) ----
+            const uint32_t key = act ? df_key(z, a) : 0u;
+            const uint32_t h = (key * 2654435761u) >> (32 - DF_HASH_BITS);
+            const int32_t  oldhead = act ? z.head[h] : -1;
+            int64_t p = oldhead, found = -1;
+            if (act)
+                while (p >= 0 && a - p <= z.mask) {
+                    if (df_key(z, p) == key) { found = p; break; }
+                    p = z.prevh[p & z.mask];
+                }
+            const unsigned actmask = __ballot_sync(0xffffffffu, act);
+            const unsigned below = (1u << lane) - 1u;
+            const unsigned pk = __match_any_sync(0xffffffffu, key) & actmask;
+            const unsigned ph = __match_any_sync(0xffffffffu, h) & actmask;
+            const int64_t nxt = (pk & below) ? a0 + (31 - __clz(pk & below)) : found;
+            const int64_t prv = (ph & below) ? a0 + (31 - __clz(ph & below)) : (int64_t)oldhead;
+            // the window slots this batch overwrites still belong to positions one window back,
+            // which an earlier lane's chain walk may yet have to read: keep their links
+            if (act) S.win[lane] = (uint32_t)z.next[a & z.mask];
+            __syncwarp();
+            if (act) {
+                z.next[a & z.mask]  = (int32_t)nxt;
+                z.prevh[a & z.mask] = (int32_t)prv;
+                if ((int)lane == 31 - __clz(ph)) z.head[h] = (int32_t)a;
             }
+            for (int r = 0; r < nb; ++r)  // DeflatorMatches.store(vertex:) for the batch, one row per store
+                g[((z.count + r) << 5) + lane] = lane == 0 ? (uint32_t)z.x[a0 + r] : 0u;
+            __syncwarp();
+            // ---- (M) ----
+            int extent = 1;
+            if (act && nxt >= 0) {
+                const int limit = (int)(z.n - a < 258 ? z.n - a : 258);
+                int64_t   current = nxt, distance = a - current;
+                long      remaining = z.attempts;
+                uint32_t* edges = g + ((z.count + lane) << 5) + 2;
+                for (;;) {
+                    int run = 4;
+                    while (run < limit && z.x[current + run] == z.x[a + run]) ++run;
+                    if (run > extent) extent = run;
+                    const uint32_t dd = df_dist_decade((uint32_t)distance);
+                    if ((uint32_t)run > (edges[dd] & 0xffffu)) edges[dd] = (uint32_t)distance << 16 | (uint32_t)run;
+                    remaining -= 1;
+                    if (!(remaining > 0 && z.goal > run)) break;
+                    const int64_t q = current + z.mask + 1 - a0;  // lane that overwrote this slot, if any
+                    const int64_t nx = (q > (int64_t)lane && q < nb) ? (int64_t)(int32_t)S.win[q]
+                                                                    : (int64_t)z.next[current & z.mask];
+                    if (nx < 0) break;
+                    distance += current - nx;
+                    current = nx;
+                    if (!(distance < z.mask)) break;
+                }
+            }
+            __syncwarp();
+            // ---- (S) skip rule: after a match longer than 100 the next min(extent - 100, unfilled)
+            //      vertices carry no edges (and do not trigger the rule themselves) ----
+            for (int l = 0; l < nb; ++l) {
+                const int     ext = __shfl_sync(0xffffffffu, extent, l);
+                const int64_t al = a0 + l;
+                if (al < z.skip_until) {
+                    if (lane >= 2) g[((z.count + l) << 5) + lane] = 0u;
+                } else if (ext > 100) {
+                    const int64_t unf_after = z.limit - 1 - (z.count + l + 1);
+                    z.skip_until = al + 1 + (ext - 100 < unf_after ? ext - 100 : unf_after);
+                }
+            }
+            __syncwarp();
+            z.count += nb;
+            z.end_index += nb;
+            z.dequeued += nb;
         }
     }
     int64_t epilogue = -3 - (z.end_index < 0 ? z.end_index : 0);
@@ -749,7 +811,7 @@ __global__ void __launch_bounds__(32) deflate_kernel(DfParams P)
         z.x = job.src; z.n = (int64_t)job.n;
         int exponent = job.format == PNGB200_FORMAT_IOS ? 15 : job.exponent;
         z.mask = ((int64_t)1 << exponent) - 1;
-        z.end_index = -3; z.dequeued = 0; z.count = 0; z.limit = 2048; z.generic = 1;
+        z.end_index = -3; z.dequeued = 0; z.count = 0; z.limit = 2048; z.generic = 1; z.skip_until = 0;
         z.head  = reinterpret_cast<int32_t*>(slot);
         z.prevh = z.head + (1 << DF_HASH_BITS);
         z.next  = z.prevh + 32768;
