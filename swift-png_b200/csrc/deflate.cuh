@@ -275,7 +275,8 @@ struct DfState {
     const uint8_t* x;
     int64_t  n, mask, end_index, dequeued;
     int32_t *head, *prevh, *next;
-    uint32_t* graph;   // 32 x u32 per vertex: upstream, depth(unused on device), 30 edges
+    uint32_t* graph;   // 32 x u32 per vertex: (unused), (unused), 30 edges: distance << 16 | longest run
+    uint32_t* up;      // upstream word per vertex (+1 for the sink)
     int64_t  limit, capacity, count, skip_until;
     int      mode, goal, iterations, generic;
     long     attempts;
@@ -510,35 +511,37 @@ __device__ bool df_compress(DfState& z, DfShared& S)
 __device__ void df_minimize(DfState& z, DfShared& S)
 {
     const unsigned lane = lane_id();
-    uint32_t* g = z.graph;
-    const int64_t count = z.count;
+    uint32_t* g  = z.graph;   // 32 words per vertex; words 2..31 = best edge per distance decade
+    uint32_t* up = z.up;      // upstream word per vertex: length << 16 | decade << 8
+    const int64_t  count = z.count;
+    const uint8_t* lits  = z.x + (z.end_index - z.count);  // vertex v is input position pos0 + v
     for (uint32_t i = lane; i < DF_RING; i += 32) S.ring[i] = 0xffffffffu;
     for (uint32_t i = lane; i < 320; i += 32) S.freq[i] = 0;
     __syncwarp();
     if (lane == 0) S.ring[0] = 0;
     __syncwarp();
-    // ---- explore every vertex in order; costs live in the ring, upstream words in HBM ----
-    uint32_t row = count > 0 ? g[lane] : 0;  // vertex 0: upstream, (unused), edges
+    // ---- explore every vertex in order; path costs live in the shared-memory ring, upstream words
+    //      are write-only here; edge rows are prefetched four vertices ahead ----
+    uint32_t r0 = 0 < count ? g[(0 << 5) + lane] : 0, r1 = 1 < count ? g[(1 << 5) + lane] : 0;
+    uint32_t r2 = 2 < count ? g[(2 << 5) + lane] : 0, r3 = 3 < count ? g[(3 << 5) + lane] : 0;
     for (int64_t s = 0; s < count; ++s) {
-        uint32_t nrow = s + 1 < count ? g[((s + 1) << 5) + lane] : 0;  // prefetch the next vertex
+        const uint32_t row = r0;
+        r0 = r1; r1 = r2; r2 = r3;
+        r3 = s + 4 < count ? g[((s + 4) << 5) + lane] : 0;
         const uint32_t cur_depth = S.ring[s & (DF_RING - 1)];
-        const uint32_t lit = __shfl_sync(0xffffffffu, row, 0) & 0xffu;
         const int64_t  remaining = count - s;
-        // the slot 259+ ahead is recycled for a vertex not reached yet
-        if (lane == 0) S.ring[(s + 512) & (DF_RING - 1)] = 0xffffffffu;
-        // literal edge (length 1)
         if (lane == 0) {
-            uint32_t ld = cur_depth + S.depths[lit];
+            S.ring[(s + 512) & (DF_RING - 1)] = 0xffffffffu;  // recycle a slot far ahead
+            const uint32_t ld = cur_depth + S.depths[lits[s]];   // literal edge (length 1)
             uint32_t& nd = S.ring[(s + 1) & (DF_RING - 1)];
             if (ld < nd) {
                 nd = ld;
-                g[(s + 1) << 5] = 0x0001ff00u | (g[(s + 1) << 5] & 0xffu);
+                up[s + 1] = 0x0001ff00u;
             }
         }
-        // which decades have an edge
         uint32_t myrun = (lane >= 2 && remaining >= 3) ? (row & 0xffffu) : 0;
         if ((int64_t)myrun > remaining) myrun = (uint32_t)remaining;
-        unsigned present = __ballot_sync(0xffffffffu, myrun > 0);
+        const unsigned present = __ballot_sync(0xffffffffu, myrun > 0);
         if (present) {
             uint32_t maxrun = myrun;
             for (int o = 16; o; o >>= 1) maxrun = max(maxrun, __shfl_xor_sync(0xffffffffu, maxrun, o));
@@ -547,11 +550,11 @@ __device__ void df_minimize(DfState& z, DfShared& S)
                 uint32_t best = 0xffffffffu, bdec = 0;
                 unsigned m = present;
                 while (m) {   // decades ascending: a later decade must be strictly cheaper to win
-                    int      dl = __ffs(m) - 1;
+                    const int dl = __ffs(m) - 1;
                     m &= m - 1;
-                    uint32_t r = __shfl_sync(0xffffffffu, myrun, dl);
+                    const uint32_t r = __shfl_sync(0xffffffffu, myrun, dl);
                     if (len <= r) {
-                        uint32_t d = cur_depth + S.depths[512 + dl - 2] + S.depths[253 + len];
+                        const uint32_t d = cur_depth + S.depths[512 + dl - 2] + S.depths[253 + len];
                         if (d < best) { best = d; bdec = (uint32_t)(dl - 2); }
                     }
                 }
@@ -559,34 +562,32 @@ __device__ void df_minimize(DfState& z, DfShared& S)
                     uint32_t& nd = S.ring[(s + len) & (DF_RING - 1)];
                     if (best < nd) {
                         nd = best;
-                        uint32_t* up = g + ((s + len) << 5);
-                        *up = len << 16 | bdec << 8 | (*up & 0xffu);
+                        up[s + len] = len << 16 | bdec << 8;
                     }
                 }
             }
         }
         __syncwarp();
-        row = nrow;
     }
     __syncwarp();
     // ---- walk back from the sink, reverse the links, tally symbol frequencies ----
     if (count > 0) {
         int64_t  ci = count;
-        uint32_t cu = g[ci << 5];
+        uint32_t cu = up[ci];
         int64_t  wlo = -1;  // window [wlo, wlo + 768) of upstream words in shared memory
         do {
-            int64_t length = cu >> 16;
-            int64_t ni = ci - length;
+            const int64_t length = cu >> 16;
+            const int64_t ni = ci - length;
             if (wlo < 0 || ni < wlo) {
                 __syncwarp();
                 wlo = ni - 767 > 0 ? ni - 767 : 0;
-                for (int64_t k = wlo + lane; k <= ni; k += 32) S.win[k - wlo] = g[k << 5];
+                for (int64_t k = wlo + lane; k <= ni; k += 32) S.win[k - wlo] = up[k];
                 __syncwarp();
             }
-            uint32_t nu = S.win[ni - wlo];
+            const uint32_t nu = S.win[ni - wlo];
             if (lane == 0) {
-                g[ni << 5] = (cu & 0xffffff00u) | (nu & 0xffu);
-                if (length == 1) S.freq[nu & 0xff] += 1;
+                up[ni] = cu;
+                if (length == 1) S.freq[lits[ni]] += 1;
                 else {
                     S.freq[256 | df_run_decade((uint32_t)length)] += 1;
                     S.freq[288 + ((cu >> 8) & 0xff)] += 1;
@@ -760,6 +761,8 @@ __device__ int df_write_block(DfState& z, DfShared& S, DfOut& out, bool final)
         z.count = 0;
     } else {
         uint32_t* g = z.graph;
+        const uint32_t* up = z.up;
+        const uint8_t*  lits = z.x + (z.end_index - z.count);
         int64_t index = 0, whi = -1;  // window [wlo, whi) of upstream words
         int64_t wlo = 0;
         while (index < z.count) {
@@ -767,14 +770,14 @@ __device__ int df_write_block(DfState& z, DfShared& S, DfOut& out, bool final)
                 __syncwarp();
                 wlo = index;
                 whi = index + 768 < z.count ? index + 768 : z.count;
-                for (int64_t k = wlo + lane; k < whi; k += 32) S.win[k - wlo] = g[k << 5];
+                for (int64_t k = wlo + lane; k < whi; k += 32) S.win[k - wlo] = up[k];
                 __syncwarp();
             }
-            uint32_t up = S.win[index - wlo];
-            int64_t  cnt = up >> 16;
-            if (cnt == 1) out.put(S.cw_bits[up & 0xff], S.cw_len[up & 0xff]);
+            uint32_t upw = S.win[index - wlo];
+            int64_t  cnt = upw >> 16;
+            if (cnt == 1) { const uint32_t lit = lits[index]; out.put(S.cw_bits[lit], S.cw_len[lit]); }
             else {
-                uint32_t rd = df_run_decade((uint32_t)cnt), dd = (up >> 8) & 0xff;
+                uint32_t rd = df_run_decade((uint32_t)cnt), dd = (upw >> 8) & 0xff;
                 uint32_t offset = g[(index << 5) + 2 + dd] >> 16;
                 out.put(S.cw_bits[256 | rd], S.cw_len[256 | rd]);
                 out.put((uint32_t)cnt - c_len_base[rd - 1], c_len_extra[rd - 1]);
@@ -816,6 +819,7 @@ __global__ void __launch_bounds__(32) deflate_kernel(DfParams P)
         z.prevh = z.head + (1 << DF_HASH_BITS);
         z.next  = z.prevh + 32768;
         z.graph = reinterpret_cast<uint32_t*>(z.next + 32768);
+        z.up    = z.graph + 32 * P.graph_vertices;
         {   // DeflatorSearch.init(level:)
             const int lv = job.level <= 0 ? 0 : job.level;
             const long AT[13] = {1, 2, 4, 40, 20, 40, 64, 100, 14, 20, 30, 60, 100};
@@ -904,7 +908,7 @@ __global__ void __launch_bounds__(32) deflate_kernel(DfParams P)
 
 inline uint64_t df_scratch_stride(uint64_t graph_vertices)
 {
-    uint64_t s = 4ull * ((1u << DF_HASH_BITS) + 2 * 32768) + 128ull * graph_vertices;
+    uint64_t s = 4ull * ((1u << DF_HASH_BITS) + 2 * 32768) + 132ull * graph_vertices;
     return (s + 255) / 256 * 256;
 }
 
