@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--mode", default="decode", choices=["decode", "encode"])
     ap.add_argument("--encode-level", type=int, default=9)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: <= 8 GB pinned)")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: whole batch if <= 110 GB pinned)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-images", type=int, default=0)
     return ap.parse_args()
@@ -292,7 +292,7 @@ def main():
         import psutil
         per_image = storage_bytes + max(len(it["idat"]) for it in items)
         avail = psutil.virtual_memory().available
-        EB = min(B, args.e2e_batch) if args.e2e_batch else (B if per_image * B < (8 << 30) else max(8, (8 << 30) // per_image))
+        EB = min(B, args.e2e_batch) if args.e2e_batch else (B if per_image * B < (110 << 30) else max(8, (110 << 30) // per_image))
         while EB > 8 and EB * per_image * 2.5 * max(world, 1) > avail:
             EB //= 2  # pinned host staging for the whole batch must fit comfortably in host RAM
         full_B, B = B, EB

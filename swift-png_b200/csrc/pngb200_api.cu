@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "checksum.cuh"
@@ -101,6 +102,9 @@ struct pngb200_ctx {
     std::vector<uint64_t> expected;   // filtered bytes expected per image
     std::vector<size_t>   out_offset; // staging offsets (HOST memspace)
     std::vector<size_t>   out_bytes;
+    // helper contexts (own stream + workspaces) that pipeline big host-memory batches: while one
+    // lane's PCIe copies run, another lane's kernels do
+    std::vector<pngb200_ctx*> lanes;
 };
 
 namespace {
@@ -407,6 +411,8 @@ pngb200_ctx* pngb200_ctx_create(int device)
 void pngb200_ctx_destroy(pngb200_ctx* ctx)
 {
     if (!ctx) return;
+    for (pngb200_ctx* lane : ctx->lanes) pngb200_ctx_destroy(lane);
+    ctx->lanes.clear();
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->d_jobs, &ctx->d_results, &ctx->d_imgjobs, &ctx->d_genjobs, &ctx->d_misc,
@@ -423,7 +429,13 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
 const char* pngb200_last_error(const pngb200_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
 void*       pngb200_ctx_stream(pngb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int         pngb200_ctx_device(const pngb200_ctx* ctx) { return ctx ? ctx->device : -1; }
-uint64_t    pngb200_ctx_launch_count(const pngb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t    pngb200_ctx_launch_count(const pngb200_ctx* ctx)
+{
+    if (!ctx) return 0;
+    uint64_t n = ctx->launches;
+    for (const pngb200_ctx* lane : ctx->lanes) n += lane->launches;
+    return n;
+}
 void        pngb200_ctx_set_inflate_mode(pngb200_ctx* ctx, int mode) { if (ctx) ctx->inflate_mode = mode; }
 
 int pngb200_ctx_inflate_stats(pngb200_ctx* ctx, size_t count, uint64_t out[4])
@@ -630,9 +642,55 @@ int pngb200_decode_batch_finish(pngb200_ctx* ctx, pngb200_image_desc* im, size_t
 
 int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)
 {
-    int rc = pngb200_decode_batch_enqueue(ctx, im, count, memspace);
-    if (rc != PNGB200_OK) return rc;
-    return pngb200_decode_batch_finish(ctx, im, count);
+    if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    // Host-memory batches with a lot of bytes to move are cut into chunks that three lanes (helper
+    // contexts on the same GPU, one host thread each) work through round-robin, so that one chunk's
+    // H2D / D2H copies overlap another chunk's kernels.  Results are identical: images are
+    // independent units.
+    size_t bytes = 0;
+    for (size_t i = 0; i < count; ++i)
+        bytes += im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume);
+    constexpr size_t kLanes = 3, kMinChunk = 32;
+    if (memspace != PNGB200_MEM_HOST || count < 2 * kMinChunk || bytes < ((size_t)256 << 20)) {
+        int rc = pngb200_decode_batch_enqueue(ctx, im, count, memspace);
+        if (rc != PNGB200_OK) return rc;
+        return pngb200_decode_batch_finish(ctx, im, count);
+    }
+    while (ctx->lanes.size() < kLanes) {
+        pngb200_ctx* lane = pngb200_ctx_create(ctx->device);
+        if (!lane) return set_error(ctx, PNGB200_ERR_CUDA, "cannot create a pipeline lane: %s", g_last_error.c_str());
+        lane->inflate_mode = ctx->inflate_mode;
+        ctx->lanes.push_back(lane);
+    }
+    const size_t nchunks = std::min<size_t>(count / kMinChunk, 4 * kLanes);
+    std::vector<size_t> cut(nchunks + 1);  // chunk boundaries balanced by bytes
+    {
+        size_t acc = 0, k = 1;
+        cut[0] = 0;
+        for (size_t i = 0; i < count && k < nchunks; ++i) {
+            acc += im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume);
+            if (acc * nchunks >= bytes * k) cut[k++] = i + 1;
+        }
+        while (k <= nchunks) cut[k++] = count;
+    }
+    std::vector<int> rcs(kLanes, PNGB200_OK);
+    std::vector<std::thread> workers;
+    for (size_t l = 0; l < kLanes; ++l)
+        workers.emplace_back([&, l]() {
+            pngb200_ctx* lane = ctx->lanes[l];
+            lane->inflate_mode = ctx->inflate_mode;
+            for (size_t c = l; c < nchunks; c += kLanes) {
+                size_t lo = cut[c], n = cut[c + 1] - cut[c];
+                if (n == 0) continue;
+                int rc = pngb200_decode_batch_enqueue(lane, im + lo, n, PNGB200_MEM_HOST);
+                if (rc == PNGB200_OK) rc = pngb200_decode_batch_finish(lane, im + lo, n);
+                if (rc != PNGB200_OK) { rcs[l] = rc; ctx->error = lane->error; return; }
+            }
+        });
+    for (std::thread& t : workers) t.join();
+    for (int rc : rcs)
+        if (rc != PNGB200_OK) return rc;
+    return PNGB200_OK;
 }
 
 int pngb200_unfilter_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)

@@ -286,3 +286,20 @@ def test_decode_reference_encoded_streams_large_blocks(pngb200, ctx, orc):
             ctx.set_inflate_mode(0)
         for g, ref in zip(got, want):
             assert g.status == 0 and g.pixels == ref
+
+
+def test_host_batch_pipelined_over_lanes(pngb200, ctx, orc):
+    """big host-memory batches are cut into chunks worked through by helper lanes (copy/compute
+    overlap); results must be the same as the single-lane path, image by image"""
+    w, h = 1024, 1024
+    imgs = [corpus.make(kind, w, h, i) for i, kind in enumerate(["photo", "graphic", "noise", "photo"])]
+    streams = [corpus.zlib_png_stream(im, 4, 6)[1] for im in imgs]
+    jobs = [dict(idat=streams[i % 4], width=w, height=h, volume=32, depth=8) for i in range(72)]
+    jobs[5] = dict(jobs[5], idat=jobs[5]["idat"][:-7])          # one truncated stream in the middle
+    got = pngb200.decode_batch(ctx, jobs)
+    for i, g in enumerate(got):
+        if i == 5:
+            assert g.status == pngb200.ERR_PNG_INCOMPLETE_DATASTREAM
+        else:
+            assert g.status == 0 and g.pixels == imgs[i % 4].tobytes(), i
+    assert ctx.launches > 0
