@@ -96,6 +96,7 @@ struct pngb200_ctx {
     DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order, d_scratch, d_dfscratch, d_dfjobs, d_dfres, d_enc;
     // pinned host tables
     PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order;
+    uint64_t scratch_stride = 0;       // layout of d_scratch the last inflate launch used
     size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // decode stage boundaries
     // geometry of the pending decode batch
@@ -178,9 +179,13 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             pp.scratch_stride = par_scratch_stride(pp.bitmap_words);
             unsigned grid = (unsigned)std::min<size_t>(par.size(), (size_t)ctx->sm_count * PAR_CTAS_PER_SM);
             size_t need = (size_t)pp.scratch_stride * grid + 256;
-            if (need > ctx->d_scratch.cap) {  // fresh scratch must start zeroed (the kernel keeps it clean)
+            // The per-CTA "unresolved" bitmaps must be all-zero when a launch starts; the kernel
+            // leaves them clean.  A different stride moves the bitmaps onto bytes that held copy
+            // lists before, and a fresh allocation is garbage: zero the whole arena in both cases.
+            if (need > ctx->d_scratch.cap || pp.scratch_stride != ctx->scratch_stride) {
                 CU(ctx->d_scratch.reserve(need));
                 CU(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, ctx->stream));
+                ctx->scratch_stride = pp.scratch_stride;
             }
             pp.ticket = (uint32_t*)((char*)ctx->d_scratch.p + (size_t)pp.scratch_stride * grid);
             CU(cudaMemsetAsync(pp.ticket, 0, sizeof(uint32_t), ctx->stream));
