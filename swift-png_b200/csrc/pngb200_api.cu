@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -655,7 +656,10 @@ int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count,
     size_t bytes = 0;
     for (size_t i = 0; i < count; ++i)
         bytes += im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume);
-    constexpr size_t kLanes = 3, kMinChunk = 32;
+    // lanes / chunks per lane: tunable for experiments (PNGB200_LANES, PNGB200_CHUNKS_PER_LANE)
+    static const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 3;
+    static const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(1, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 4;
+    constexpr size_t kMinChunk = 32;
     if (memspace != PNGB200_MEM_HOST || count < 2 * kMinChunk || bytes < ((size_t)256 << 20)) {
         int rc = pngb200_decode_batch_enqueue(ctx, im, count, memspace);
         if (rc != PNGB200_OK) return rc;
@@ -667,7 +671,7 @@ int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count,
         lane->inflate_mode = ctx->inflate_mode;
         ctx->lanes.push_back(lane);
     }
-    const size_t nchunks = std::min<size_t>(count / kMinChunk, 4 * kLanes);
+    const size_t nchunks = std::min<size_t>(count / kMinChunk, kPerLane * kLanes);
     std::vector<size_t> cut(nchunks + 1);  // chunk boundaries balanced by bytes
     {
         size_t acc = 0, k = 1;
