@@ -150,11 +150,21 @@ __global__ void __launch_bounds__(32) checksum_fold_kernel(ChecksumParams p)
     const uint32_t  nch  = (uint32_t)((n + CK_CHUNK - 1) / CK_CHUNK);
     uint32_t computed;
     if (job.format == PNGB200_FORMAT_GZIP) {
+        // crc(A || B) = shift(crc(A), |B|) ^ crc(B).  All chunks but the last are CK_CHUNK long, so
+        // the shift operator for CK_CHUNK bytes is built once (squarings) and applied per chunk
         computed = 0;
-        if (lane == 0)
-            for (uint32_t c = 0; c < nch; ++c)
-                computed = crc32_combine(computed, (uint32_t)p.partial[2 * (uint64_t)(c0 + c)],
-                                         p.partial[2 * (uint64_t)(c0 + c) + 1]);
+        if (lane == 0) {
+            uint32_t op[32], tmp[32];  // GF(2) operator for "append CK_CHUNK zero bytes"
+            op[0] = 0xEDB88320u;
+            for (int n = 1; n < 32; ++n) op[n] = 1u << (n - 1);       // one zero BIT
+            for (int k = 0; k < 3; ++k) { gf2_square(tmp, op); for (int n = 0; n < 32; ++n) op[n] = tmp[n]; }  // one byte
+            for (uint32_t len = 1; len < CK_CHUNK; len <<= 1) { gf2_square(tmp, op); for (int n = 0; n < 32; ++n) op[n] = tmp[n]; }
+            for (uint32_t c = 0; c < nch; ++c) {
+                const uint32_t crc2 = (uint32_t)p.partial[2 * (uint64_t)(c0 + c)];
+                const uint64_t len2 = p.partial[2 * (uint64_t)(c0 + c) + 1];
+                computed = len2 == CK_CHUNK ? (gf2_times(op, computed) ^ crc2) : crc32_combine(computed, crc2, len2);
+            }
+        }
         computed = __shfl_sync(0xffffffffu, computed, 0);
     } else {
         uint64_t s1 = 0, s2 = 0;

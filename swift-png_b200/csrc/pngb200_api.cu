@@ -649,15 +649,16 @@ int pngb200_decode_batch_finish(pngb200_ctx* ctx, pngb200_image_desc* im, size_t
 int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)
 {
     if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
-    // Host-memory batches with a lot of bytes to move are cut into chunks that three lanes (helper
-    // contexts on the same GPU, one host thread each) work through round-robin, so that one chunk's
+    // Host-memory batches with a lot of bytes to move are cut into chunks that four lanes (helper
+    // contexts on the same GPU, one host thread each; measured r01: 1/3/4/6 lanes = 5.6/6.8/7.1/6.6
+    // GPixels/s end to end on 1184 x 1080p) work through round-robin, so that one chunk's
     // H2D / D2H copies overlap another chunk's kernels.  Results are identical: images are
     // independent units.
     size_t bytes = 0;
     for (size_t i = 0; i < count; ++i)
         bytes += im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume);
     // lanes / chunks per lane: tunable for experiments (PNGB200_LANES, PNGB200_CHUNKS_PER_LANE)
-    static const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 3;
+    static const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 4;
     static const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(1, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 4;
     constexpr size_t kMinChunk = 32;
     if (memspace != PNGB200_MEM_HOST || count < 2 * kMinChunk || bytes < ((size_t)256 << 20)) {

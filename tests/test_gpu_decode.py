@@ -303,3 +303,23 @@ def test_host_batch_pipelined_over_lanes(pngb200, ctx, orc):
         else:
             assert g.status == 0 and g.pixels == imgs[i % 4].tobytes(), i
     assert ctx.launches > 0
+
+
+def test_inflate_large_gzip_and_zlib_streams(pngb200, ctx, orc):
+    """config 5 shape: standalone multi-MB streams (many blocks, thousands of waves, CRC-32 folded over
+    ~1000 chunks); the 48 MB stream is also compared block count for block count with the oracle"""
+    import gzip as gz
+    rng = np.random.default_rng(9)
+    base = corpus.make("photo", 1024, 1024, 11).tobytes()
+    big = (base * 12)[: 48 * 1024 * 1024 + 12345]
+    streams = [gz.compress(big, 6), zlib.compress(big[: 5_000_001], 9), gz.compress(bytes(rng.integers(0, 256, 3_000_000, dtype=np.uint8)), 1)]
+    plain = [big, big[: 5_000_001], None]
+    fmts = [pngb200.FORMAT_GZIP, pngb200.FORMAT_ZLIB, pngb200.FORMAT_GZIP]
+    got = pngb200.inflate_batch(ctx, streams, fmts, caps=[len(big), 5_000_001, 3_000_000])
+    for i, (st, out, d) in enumerate(got):
+        assert st == 0, (i, st)
+        ref = plain[i] if plain[i] is not None else gz.decompress(streams[i])
+        assert out == ref
+        assert d.checksum == (zlib.crc32(ref) if fmts[i] == pngb200.FORMAT_GZIP else zlib.adler32(ref))
+    ost, oout, ores = orc.inflate(streams[1])
+    assert ost == 0 and got[1][2].blocks == ores.blocks and got[1][2].consumed_bits == ores.consumed_bits
