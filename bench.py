@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: whole batch if <= 110 GB pinned)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-sweep", default="", help="experiment: comma list of LANESxCHUNKS_PER_LANE to time the host leg with")
     ap.add_argument("--cpu-images", type=int, default=0)
     return ap.parse_args()
 
@@ -314,6 +315,7 @@ def main():
             at += n
         del d_pixels
         torch.cuda.empty_cache()
+        ctx.trim()  # the device-resident leg's arenas would otherwise sit beside the lanes'
 
         def step_host():
             ctx.check(L.pngb200_decode_batch(ctx.handle, hdescs, B, pkg.MEM_HOST))
@@ -335,6 +337,23 @@ def main():
                "images_per_gpu": B,
                "note": "pngb200_decode_batch with pinned HOST buffers: H2D of the IDAT streams and D2H of the "
                        "decoded pixels are inside the timed region (host wall clock, max over ranks)"}
+        if args.e2e_sweep:
+            sweep = {}
+            for cfg in args.e2e_sweep.split(","):
+                ln, ck = cfg.split("x")
+                os.environ["PNGB200_LANES"], os.environ["PNGB200_CHUNKS_PER_LANE"] = ln, ck
+                try:
+                    ctx.trim()
+                    step_host()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(2):
+                        step_host()
+                    sweep[cfg] = B * npix * 2 / (time.perf_counter() - t0) / 1e6
+                except Exception as exc:  # e.g. a chunking that does not fit the device
+                    sweep[cfg] = "failed: %s" % (str(exc)[:80],)
+            e2e["sweep"] = sweep
+            os.environ.pop("PNGB200_LANES"), os.environ.pop("PNGB200_CHUNKS_PER_LANE")
         B = full_B
 
     if rank != 0:

@@ -56,6 +56,7 @@ typedef enum pngb200_status {
     PNGB200_ERR_PNG_EXTRANEOUS_IMAGE_DATA        = -48,
     PNGB200_ERR_PNG_EXTRANEOUS_COMPRESSED_DATA   = -49,
     PNGB200_ERR_PNG_INCOMPLETE_DATASTREAM        = -50,
+    PNGB200_ERR_PNG_PALETTE_INDEX                = -51, /* indexed pixel beyond the palette: the reference traps */
     /* API-level */
     PNGB200_ERR_OUTPUT_CAPACITY                  = -64,
     PNGB200_ERR_BAD_ARGUMENT                     = -65,
@@ -79,6 +80,9 @@ typedef struct pngb200_ctx pngb200_ctx;
  * sm_100 device, out of memory); pngb200_last_error(NULL) then describes why. */
 pngb200_ctx* pngb200_ctx_create(int device);
 void         pngb200_ctx_destroy(pngb200_ctx* ctx);
+/* Return the context's grow-only device arenas (and its pipeline lanes') to the driver; the next
+ * batch call allocates again.  Fails with BAD_ARGUMENT while a decode batch is pending. */
+int          pngb200_ctx_trim(pngb200_ctx* ctx);
 const char*  pngb200_last_error(const pngb200_ctx* ctx);
 /* the cudaStream_t all of this context's work is enqueued on (for event timing / interop) */
 void*        pngb200_ctx_stream(pngb200_ctx* ctx);
@@ -166,6 +170,45 @@ typedef struct pngb200_filter_desc {
 } pngb200_filter_desc;
 
 int pngb200_filter_batch(pngb200_ctx* ctx, pngb200_filter_desc* images, size_t count, int memspace);
+
+/* ---- colour targets ------------------------------------------------
+ * image.unpack(as: PNG.RGBA<T>.self) / PNG.VA<T> and PNG.Image.init(packing:size:layout:) with the
+ * default deindexer / indexer, T = UInt8 or UInt16: Sources/PNG/ColorTargets/PNG.RGBA.swift:262-478,
+ * PNG.VA.swift, PNG.Color.swift, over the convolve / deconvolve closures of Sources/PNG/PNG.swift:149-1285.
+ * The unpack is inside the reference's own timed decode loop (Benchmarks/Decompression/Swift/Main.swift:105-106).
+ * For rgba8 -> RGBA<UInt8> and va8 -> VA<UInt8> the unpacked array IS PNG.Image.storage, byte for
+ * byte, so pngb200_decode_batch's output needs no second pass. */
+typedef enum pngb200_target {
+    PNGB200_TARGET_RGBA8 = 0, PNGB200_TARGET_RGBA16 = 1, PNGB200_TARGET_VA8 = 2, PNGB200_TARGET_VA16 = 3
+} pngb200_target;
+/* applied per pixel after unpacking: .premultiplied / .straightened (PNG.RGBA.swift:115-121, 163-169),
+ * or premultiplied(as: UInt8.self) / straightened(as: UInt8.self) of a 16-bit target (:141-155, 187-201) */
+typedef enum pngb200_alpha_mode {
+    PNGB200_ALPHA_ASIS = 0, PNGB200_ALPHA_PREMULTIPLIED = 1, PNGB200_ALPHA_STRAIGHTENED = 2,
+    PNGB200_ALPHA_PREMULTIPLIED_AS8 = 3, PNGB200_ALPHA_STRAIGHTENED_AS8 = 4
+} pngb200_alpha_mode;
+/* PNG.Format (Sources/PNG/Formats/PNG.Format.swift:6-43) as these kernels see it */
+typedef struct pngb200_pixel_format {
+    uint8_t        color;         /* PNG colour type: 0 v, 2 rgb, 3 indexed, 4 va, 6 rgba */
+    uint8_t        depth;         /* bits per sample: 1, 2, 4, 8, 16 */
+    uint8_t        bgr;           /* 1: .bgr8 / .bgra8 (the ios standard's sample order) */
+    uint8_t        has_key;       /* chroma key present (v / rgb / bgr formats) */
+    uint16_t       key[3];        /* raw sample values in STORAGE order (Format.recognize, :161-330) */
+    uint16_t       palette_count; /* indexed formats: entries in `palette` */
+    const uint8_t* palette;       /* palette_count x (r, g, b, a), tRNS merged; always HOST memory */
+} pngb200_pixel_format;
+typedef struct pngb200_color_desc {
+    void*                storage;      /* PNG.Image.storage: unpack reads it, pack writes it */
+    size_t               storage_len;  /* bytes (capacity for pack) */
+    void*                pixels;       /* [RGBA<T>] / [VA<T>]: native-endian T components, aligned to the pixel size */
+    size_t               pixels_len;   /* bytes (capacity for unpack) */
+    uint64_t             count;        /* number of pixels */
+    pngb200_pixel_format format;
+    int32_t              status;       /* out: PNGB200_OK or PNGB200_ERR_PNG_PALETTE_INDEX */
+} pngb200_color_desc;
+int pngb200_unpack_batch(pngb200_ctx* ctx, pngb200_color_desc* images, size_t count, int target,
+                         int alpha_mode, int memspace);
+int pngb200_pack_batch(pngb200_ctx* ctx, pngb200_color_desc* images, size_t count, int target, int memspace);
 
 /* Encode-side stage 2: LZ77.Deflator(format:level:exponent:hint:).push(src, last: true) and the
  * concatenation of every pull() -- the reference's compressed bytes, bit for bit (its output does

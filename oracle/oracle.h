@@ -112,6 +112,43 @@ size_t orc_deflate_bound(size_t n);
 size_t orc_debug_greedy_parse(const uint8_t* in, size_t n, int exponent, long attempts, int goal,
                               int* runs, int* dists, size_t cap);
 
+/* ---- colour targets -------------------------------------------
+ * PNG.Format as the unpack/pack kernels see it (Sources/PNG/Formats/PNG.Format.swift:6-43):
+ * colour type + sample depth, sample order (bgr = 1 for the ios standard's bgr8/bgra8), the
+ * chroma key in STORAGE sample order (Format.recognize, PNG.Format.swift:161-330, stores the key of
+ * a bgr8 image as (b, g, r)), and for indexed formats the (r, g, b, a) palette with tRNS merged. */
+typedef struct {
+    uint8_t        color;   /* 0 v, 2 rgb, 3 indexed, 4 va, 6 rgba */
+    uint8_t        depth;   /* 1, 2, 4, 8, 16 */
+    uint8_t        bgr;
+    uint8_t        has_key;
+    uint16_t       key[3];
+    uint16_t       palette_count;
+    const uint8_t* palette; /* palette_count x 4 bytes */
+} orc_format;
+
+enum { ORC_TARGET_RGBA8 = 0, ORC_TARGET_RGBA16 = 1, ORC_TARGET_VA8 = 2, ORC_TARGET_VA16 = 3 };
+/* 3 / 4: premultiplied(as: UInt8.self) / straightened(as: UInt8.self) of a 16-bit target
+ * (PNG.RGBA.swift:141-155, 187-201): the arithmetic runs on the high bytes, results x 257 */
+enum { ORC_ALPHA_ASIS = 0, ORC_ALPHA_PREMULTIPLIED = 1, ORC_ALPHA_STRAIGHTENED = 2,
+       ORC_ALPHA_PREMULTIPLIED_AS8 = 3, ORC_ALPHA_STRAIGHTENED_AS8 = 4 };
+enum { ORC_ERR_PALETTE_INDEX = -51 };  /* the reference traps (Swift array bounds) */
+
+/* PNG.premultiply / PNG.straighten (Sources/PNG/PNG.swift:54-120) for T = UInt8 (bits 8) or UInt16 */
+uint32_t orc_premultiply(uint32_t color, uint32_t alpha, int bits);
+uint32_t orc_straighten(uint32_t premultiplied, uint32_t alpha, int bits);
+
+/* PNG.RGBA<T>.unpack / PNG.VA<T>.unpack with the default deindexer
+ * (ColorTargets/PNG.RGBA.swift:262-365, PNG.VA.swift, PNG.Color.swift), then optionally
+ * `.premultiplied` / `.straightened` per pixel.  `storage` is PNG.Image.storage (pixels x bpp
+ * bytes, 16-bit samples big-endian, sub-byte depths one byte per sample); `out` receives native
+ * (little-endian) T components, 4 (RGBA) or 2 (VA) per pixel. */
+int orc_unpack(const uint8_t* storage, size_t pixels, const orc_format* f, int target,
+               int alpha_mode, void* out);
+/* PNG.RGBA<T>.pack / PNG.VA<T>.pack with the default indexer (PNG.RGBA.swift:405-478,
+ * PNG.Color.swift: colours missing from the palette map to entry 0) */
+int orc_pack(const void* pixels, size_t n, const orc_format* f, int target, uint8_t* storage);
+
 #ifdef __cplusplus
 }
 #endif

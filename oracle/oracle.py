@@ -39,6 +39,36 @@ ERR_PNG_INCOMPLETE_DATASTREAM = -50
 ERR_OUTPUT_CAPACITY = -64
 
 
+TARGET_RGBA8, TARGET_RGBA16, TARGET_VA8, TARGET_VA16 = 0, 1, 2, 3
+ALPHA_ASIS, ALPHA_PREMULTIPLIED, ALPHA_STRAIGHTENED, ALPHA_PREMULTIPLIED_AS8, ALPHA_STRAIGHTENED_AS8 = range(5)
+ERR_PALETTE_INDEX = -51
+
+
+class Format(C.Structure):
+    """orc_format: PNG.Format as the colour-target kernels see it."""
+    _fields_ = [
+        ("color", C.c_uint8),
+        ("depth", C.c_uint8),
+        ("bgr", C.c_uint8),
+        ("has_key", C.c_uint8),
+        ("key", C.c_uint16 * 3),
+        ("palette_count", C.c_uint16),
+        ("palette", C.c_char_p),
+    ]
+
+
+def make_format(color, depth, bgr=False, key=None, palette=None) -> Format:
+    f = Format(color=color, depth=depth, bgr=int(bgr), has_key=int(key is not None))
+    if key is not None:
+        for i, k in enumerate(key):
+            f.key[i] = k
+    if palette is not None:
+        f._keep = bytes(palette)
+        f.palette = f._keep
+        f.palette_count = len(f._keep) // 4
+    return f
+
+
 class InflateResult(C.Structure):
     _fields_ = [
         ("status", C.c_int32),
@@ -106,6 +136,14 @@ def lib():
             L.orc_debug_greedy_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_long, C.c_int,
                                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_size_t]
             L.orc_debug_greedy_parse.restype = C.c_size_t
+        L.orc_premultiply.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_premultiply.restype = C.c_uint32
+        L.orc_straighten.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_straighten.restype = C.c_uint32
+        L.orc_unpack.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(Format), C.c_int, C.c_int, C.c_void_p]
+        L.orc_unpack.restype = C.c_int
+        L.orc_pack.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(Format), C.c_int, C.c_void_p]
+        L.orc_pack.restype = C.c_int
         _lib = L
     return _lib
 
@@ -182,3 +220,34 @@ def greedy_parse(data: bytes, exponent: int, attempts: int = 2 ** 62, goal: int 
     runs, dists = (C.c_int * (n + 8))(), (C.c_int * (n + 8))()
     k = lib().orc_debug_greedy_parse(data, n, exponent, attempts, goal, runs, dists, n + 8)
     return [(runs[i], dists[i]) for i in range(k)]
+
+
+_TARGET_BYTES = {TARGET_RGBA8: 4, TARGET_RGBA16: 8, TARGET_VA8: 2, TARGET_VA16: 4}
+_CHANNELS = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}
+
+
+def unpack(storage: bytes, fmt: Format, target: int, alpha_mode: int = ALPHA_ASIS):
+    """image.unpack(as: PNG.RGBA<T> / PNG.VA<T>) [.premultiplied / .straightened].
+    Returns (status, bytes of native little-endian T components)."""
+    pixels = len(storage) // (_CHANNELS[fmt.color] * (2 if fmt.depth == 16 else 1))
+    buf = C.create_string_buffer(max(pixels * _TARGET_BYTES[target], 1))
+    st = lib().orc_unpack(storage, pixels, C.byref(fmt), target, alpha_mode, buf)
+    return st, buf.raw[: pixels * _TARGET_BYTES[target]]
+
+
+def pack(pixels: bytes, fmt: Format, target: int) -> bytes:
+    """PNG.Image(packing:size:layout:) storage of an RGBA<T> / VA<T> array."""
+    n = len(pixels) // _TARGET_BYTES[target]
+    size = n * _CHANNELS[fmt.color] * (2 if fmt.depth == 16 else 1)
+    buf = C.create_string_buffer(max(size, 1))
+    st = lib().orc_pack(pixels, n, C.byref(fmt), target, buf)
+    assert st == 0, st
+    return buf.raw[:size]
+
+
+def premultiply(color: int, alpha: int, bits: int) -> int:
+    return lib().orc_premultiply(color, alpha, bits)
+
+
+def straighten(color: int, alpha: int, bits: int) -> int:
+    return lib().orc_straighten(color, alpha, bits)

@@ -111,6 +111,29 @@ class EncodeDesc(C.Structure):
     ]
 
 
+TARGET_RGBA8, TARGET_RGBA16, TARGET_VA8, TARGET_VA16 = 0, 1, 2, 3
+ALPHA_ASIS, ALPHA_PREMULTIPLIED, ALPHA_STRAIGHTENED, ALPHA_PREMULTIPLIED_AS8, ALPHA_STRAIGHTENED_AS8 = range(5)
+ERR_PNG_PALETTE_INDEX = -51
+_TARGET_BYTES = {TARGET_RGBA8: 4, TARGET_RGBA16: 8, TARGET_VA8: 2, TARGET_VA16: 4}
+_CHANNELS = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}
+
+
+class PixelFormat(C.Structure):
+    """pngb200_pixel_format: PNG.Format as the colour-target kernels see it."""
+    _fields_ = [
+        ("color", C.c_uint8), ("depth", C.c_uint8), ("bgr", C.c_uint8), ("has_key", C.c_uint8),
+        ("key", C.c_uint16 * 3), ("palette_count", C.c_uint16), ("palette", C.c_void_p),
+    ]
+
+
+class ColorDesc(C.Structure):
+    _fields_ = [
+        ("storage", C.c_void_p), ("storage_len", C.c_size_t),
+        ("pixels", C.c_void_p), ("pixels_len", C.c_size_t),
+        ("count", C.c_uint64), ("format", PixelFormat), ("status", C.c_int32),
+    ]
+
+
 class PNGB200Error(RuntimeError):
     def __init__(self, status: int, message: str = ""):
         super().__init__(f"pngb200 status {status}: {message}")
@@ -141,6 +164,12 @@ def lib():
     L.pngb200_ctx_create.restype = C.c_void_p
     L.pngb200_ctx_destroy.argtypes = [C.c_void_p]
     L.pngb200_ctx_destroy.restype = None
+    L.pngb200_unpack_batch.argtypes = [C.c_void_p, C.POINTER(ColorDesc), C.c_size_t, C.c_int, C.c_int, C.c_int]
+    L.pngb200_unpack_batch.restype = C.c_int
+    L.pngb200_pack_batch.argtypes = [C.c_void_p, C.POINTER(ColorDesc), C.c_size_t, C.c_int, C.c_int]
+    L.pngb200_pack_batch.restype = C.c_int
+    L.pngb200_ctx_trim.argtypes = [C.c_void_p]
+    L.pngb200_ctx_trim.restype = C.c_int
     L.pngb200_last_error.argtypes = [C.c_void_p]
     L.pngb200_last_error.restype = C.c_char_p
     L.pngb200_ctx_stream.argtypes = [C.c_void_p]
@@ -216,6 +245,10 @@ class Context:
             self.handle = None
 
     __del__ = close
+
+    def trim(self):
+        """Give the grow-only device arenas back to the driver (pngb200_ctx_trim)."""
+        self.check(self._lib.pngb200_ctx_trim(self.handle))
 
     def __enter__(self):
         return self
@@ -374,6 +407,62 @@ def filter_batch(ctx: Context, images):
         descs[i].volume, descs[i].depth, descs[i].interlaced = vol, g["depth"], int(il)
     ctx.check(ctx._lib.pngb200_filter_batch(ctx.handle, descs, n, MEM_HOST))
     return [keep[i][1].raw[: keep[i][2]] for i in range(n)]
+
+
+def _fill_format(f: PixelFormat, keep: list, color, depth, bgr=False, key=None, palette=None):
+    f.color, f.depth, f.bgr, f.has_key = color, depth, int(bool(bgr)), int(key is not None)
+    for k, v in enumerate(key or ()):
+        f.key[k] = v
+    if palette is not None:
+        pal = C.create_string_buffer(bytes(palette), len(palette))
+        keep.append(pal)
+        f.palette = _buf_addr(pal)
+        f.palette_count = len(palette) // 4
+
+
+def unpack_batch(ctx: Context, images, target: int = TARGET_RGBA8, alpha_mode: int = ALPHA_ASIS):
+    """image.unpack(as: PNG.RGBA<T>.self / PNG.VA<T>.self) [.premultiplied / .straightened] over a
+    batch.  images: dicts with storage (bytes) and the PNG.Format fields color, depth[, bgr, key,
+    palette (r, g, b, a bytes)].  Returns [(status, bytes of native-endian T components)]."""
+    images = list(images)
+    n = len(images)
+    descs = (ColorDesc * n)()
+    keep = []
+    for i, g in enumerate(images):
+        st = bytes(g["storage"])
+        count = len(st) // (_CHANNELS[g["color"]] * (2 if g["depth"] == 16 else 1))
+        src = C.create_string_buffer(st, len(st)) if st else C.create_string_buffer(1)
+        dst = C.create_string_buffer(max(count * _TARGET_BYTES[target], 1))
+        keep.append((src, dst, count))
+        descs[i].storage, descs[i].storage_len = _buf_addr(src), len(st)
+        descs[i].pixels, descs[i].pixels_len = _buf_addr(dst), count * _TARGET_BYTES[target]
+        descs[i].count = count
+        _fill_format(descs[i].format, keep, g["color"], g["depth"], g.get("bgr"), g.get("key"), g.get("palette"))
+    ctx.check(ctx._lib.pngb200_unpack_batch(ctx.handle, descs, n, target, alpha_mode, MEM_HOST))
+    return [(descs[i].status, keep_i[1].raw[: keep_i[2] * _TARGET_BYTES[target]])
+            for i, keep_i in enumerate(k for k in keep if isinstance(k, tuple))]
+
+
+def pack_batch(ctx: Context, images, target: int = TARGET_RGBA8):
+    """PNG.Image(packing:size:layout:) storage of [RGBA<T>] / [VA<T>] arrays.  images: dicts with
+    pixels (bytes) and the PNG.Format fields.  Returns [bytes] (PNG.Image.storage)."""
+    images = list(images)
+    n = len(images)
+    descs = (ColorDesc * n)()
+    keep = []
+    for i, g in enumerate(images):
+        px = bytes(g["pixels"])
+        count = len(px) // _TARGET_BYTES[target]
+        size = count * _CHANNELS[g["color"]] * (2 if g["depth"] == 16 else 1)
+        src = C.create_string_buffer(px, len(px)) if px else C.create_string_buffer(1)
+        dst = C.create_string_buffer(max(size, 1))
+        keep.append((src, dst, size))
+        descs[i].pixels, descs[i].pixels_len = _buf_addr(src), len(px)
+        descs[i].storage, descs[i].storage_len = _buf_addr(dst), size
+        descs[i].count = count
+        _fill_format(descs[i].format, keep, g["color"], g["depth"], g.get("bgr"), g.get("key"), g.get("palette"))
+    ctx.check(ctx._lib.pngb200_pack_batch(ctx.handle, descs, n, target, MEM_HOST))
+    return [k[1].raw[: k[2]] for k in keep if isinstance(k, tuple)]
 
 
 def deflate_batch(ctx: Context, streams, level: int = 9, fmt: int = FORMAT_ZLIB, exponent: int = 15):

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "deflate.cuh"
 #include "filter.cuh"
+#include "color.cuh"
 #include "inflate_parallel.cuh"
 #include "inflate_serial.cuh"
 #include "unfilter.cuh"
@@ -36,7 +37,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = std::max(n + n / 4, (size_t)1 << 16);
+        size_t want = std::max(n + std::min(n / 4, (size_t)1 << 30), (size_t)1 << 16);
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             want = n;
@@ -432,6 +433,19 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
     delete ctx;
 }
 
+int pngb200_ctx_trim(pngb200_ctx* ctx)
+{
+    if (!ctx) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is pending");
+    for (pngb200_ctx* lane : ctx->lanes) pngb200_ctx_trim(lane);
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (DevBuf* b : {&ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_scratch, &ctx->d_dfscratch, &ctx->d_enc})
+        b->release();
+    ctx->scratch_stride = 0;
+    return PNGB200_OK;
+}
+
 const char* pngb200_last_error(const pngb200_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
 void*       pngb200_ctx_stream(pngb200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int         pngb200_ctx_device(const pngb200_ctx* ctx) { return ctx ? ctx->device : -1; }
@@ -658,8 +672,8 @@ int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count,
     for (size_t i = 0; i < count; ++i)
         bytes += im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume);
     // lanes / chunks per lane: tunable for experiments (PNGB200_LANES, PNGB200_CHUNKS_PER_LANE)
-    static const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 4;
-    static const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(1, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 4;
+    const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 4;
+    const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(1, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 4;
     constexpr size_t kMinChunk = 32;
     if (memspace != PNGB200_MEM_HOST || count < 2 * kMinChunk || bytes < ((size_t)256 << 20)) {
         int rc = pngb200_decode_batch_enqueue(ctx, im, count, memspace);
@@ -833,6 +847,117 @@ int pngb200_filter_batch(pngb200_ctx* ctx, pngb200_filter_desc* im, size_t count
     return PNGB200_OK;
 }
 
+}  // extern "C"
+
+// ---------------- colour targets: unpack / pack ----------------
+namespace {
+int run_color(pngb200_ctx* ctx, pngb200_color_desc* im, size_t count, int target, int alpha_mode, int memspace, bool unpack)
+{
+    if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is pending");
+    if (target < PNGB200_TARGET_RGBA8 || target > PNGB200_TARGET_VA16 || alpha_mode < PNGB200_ALPHA_ASIS ||
+        alpha_mode > PNGB200_ALPHA_STRAIGHTENED_AS8)
+        return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "bad colour target / alpha mode");
+    const bool wide_target = target == PNGB200_TARGET_RGBA16 || target == PNGB200_TARGET_VA16;
+    if (alpha_mode >= PNGB200_ALPHA_PREMULTIPLIED_AS8 && !wide_target)
+        return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "premultiplied(as: UInt8) needs a 16-bit target");
+    if (count == 0) return PNGB200_OK;
+    DeviceGuard guard(ctx->device);
+    const bool   host = memspace == PNGB200_MEM_HOST;
+    const size_t tpx  = target == PNGB200_TARGET_RGBA8 ? 4 : target == PNGB200_TARGET_RGBA16 ? 8 : target == PNGB200_TARGET_VA8 ? 2 : 4;
+    std::vector<ColorJob> jobs(count);
+    std::vector<size_t>   s_off(count), p_off(count), s_len(count);
+    std::vector<uint32_t> palettes;
+    size_t s_total = 0, p_total = 0;
+    uint64_t most = 0;
+    for (size_t i = 0; i < count; ++i) {
+        const pngb200_pixel_format& f = im[i].format;
+        const int ch = f.color == 0 || f.color == 3 ? 1 : f.color == 2 ? 3 : f.color == 4 ? 2 : f.color == 6 ? 4 : 0;
+        const bool depth_ok = f.color == 3 ? (f.depth == 1 || f.depth == 2 || f.depth == 4 || f.depth == 8)
+                            : f.color == 0 ? (f.depth == 1 || f.depth == 2 || f.depth == 4 || f.depth == 8 || f.depth == 16)
+                                           : (f.depth == 8 || f.depth == 16);
+        if (!ch || !depth_ok || (f.bgr && (f.depth != 8 || (f.color != 2 && f.color != 6))) ||
+            (f.color == 3 && (!f.palette || f.palette_count == 0 || f.palette_count > 256)) ||
+            (im[i].count && (!im[i].storage || !im[i].pixels)))
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "image %zu: bad colour descriptor", i);
+        s_len[i] = (size_t)im[i].count * ch * (f.depth == 16 ? 2 : 1);
+        if (im[i].storage_len < s_len[i] || im[i].pixels_len < im[i].count * tpx)
+            return set_error(ctx, PNGB200_ERR_OUTPUT_CAPACITY, "image %zu: buffer too small", i);
+        if (!host && (((uintptr_t)im[i].pixels) & (tpx - 1)))
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "image %zu: pixel array is not aligned to its element size", i);
+        s_off[i] = s_total, p_off[i] = p_total;
+        s_total += align_up(s_len[i] + 16, 256);
+        p_total += align_up(im[i].count * tpx + 16, 256);
+        ColorJob& j = jobs[i];
+        j.count = im[i].count;
+        j.color = f.color, j.depth = f.depth, j.bgr = f.bgr, j.has_key = f.has_key;
+        j.key[0] = f.key[0], j.key[1] = f.key[1], j.key[2] = f.key[2];
+        j.palette_off = (uint32_t)palettes.size();
+        j.palette_count = f.color == 3 ? f.palette_count : 0;
+        for (uint32_t k = 0; k < j.palette_count; ++k)
+            palettes.push_back(f.palette[4 * k] | f.palette[4 * k + 1] << 8 | f.palette[4 * k + 2] << 16 | (uint32_t)f.palette[4 * k + 3] << 24);
+        j.status = PNGB200_OK;
+        most = std::max<uint64_t>(most, im[i].count);
+    }
+    if (host) {
+        CU(ctx->d_in.reserve(unpack ? s_total : p_total));
+        CU(ctx->d_out.reserve(unpack ? p_total : s_total));
+        for (size_t i = 0; i < count; ++i) {
+            const size_t n = unpack ? s_len[i] : im[i].count * tpx;
+            if (n)
+                CU(cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + (unpack ? s_off[i] : p_off[i]), unpack ? im[i].storage : im[i].pixels,
+                                   n, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    for (size_t i = 0; i < count; ++i) {
+        uint8_t* dev_s = host ? (unpack ? ctx->d_in : ctx->d_out).as<uint8_t>() + s_off[i] : (uint8_t*)im[i].storage;
+        uint8_t* dev_p = host ? (unpack ? ctx->d_out : ctx->d_in).as<uint8_t>() + p_off[i] : (uint8_t*)im[i].pixels;
+        jobs[i].storage = dev_s, jobs[i].pixels = dev_p;
+    }
+    const size_t jb = sizeof(ColorJob) * count, off_pal = align_up(jb, 256), pb = sizeof(uint32_t) * std::max<size_t>(palettes.size(), 1);
+    CU(ctx->h_genjobs.reserve(off_pal + pb));
+    CU(ctx->d_genjobs.reserve(off_pal + pb));
+    memcpy(ctx->h_genjobs.p, jobs.data(), jb);
+    if (!palettes.empty()) memcpy((char*)ctx->h_genjobs.p + off_pal, palettes.data(), sizeof(uint32_t) * palettes.size());
+    CU(cudaMemcpyAsync(ctx->d_genjobs.p, ctx->h_genjobs.p, off_pal + pb, cudaMemcpyHostToDevice, ctx->stream));
+    ColorParams p;
+    p.jobs = ctx->d_genjobs.as<ColorJob>();
+    p.palettes = (const uint32_t*)((char*)ctx->d_genjobs.p + off_pal);
+    p.count = (uint32_t)count;
+    p.target = target;
+    p.alpha_mode = alpha_mode;
+    // x: tiles of the largest image, capped so that x * y stays near 8 CTAs per SM; y: images
+    const unsigned gy = (unsigned)std::min<size_t>(count, 65535);
+    const uint64_t tiles = std::max<uint64_t>(1, (most + COLOR_TILE - 1) / COLOR_TILE);
+    const unsigned gx = (unsigned)std::min<uint64_t>(tiles, std::max<uint64_t>(1, (uint64_t)ctx->sm_count * 8 / gy));
+    if (unpack) unpack_kernel<<<dim3(gx, gy), COLOR_THREADS, 0, ctx->stream>>>(p);
+    else pack_kernel<<<dim3(gx, gy), COLOR_THREADS, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (host)
+        for (size_t i = 0; i < count; ++i) {
+            const size_t n = unpack ? im[i].count * tpx : s_len[i];
+            if (n)
+                CU(cudaMemcpyAsync(unpack ? im[i].pixels : im[i].storage, ctx->d_out.as<uint8_t>() + (unpack ? p_off[i] : s_off[i]), n,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    CU(cudaMemcpyAsync(ctx->h_genjobs.p, ctx->d_genjobs.p, jb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const ColorJob* done = ctx->h_genjobs.as<ColorJob>();
+    for (size_t i = 0; i < count; ++i) im[i].status = done[i].status;
+    return PNGB200_OK;
+}
+}  // namespace
+
+extern "C" {
+int pngb200_unpack_batch(pngb200_ctx* ctx, pngb200_color_desc* im, size_t count, int target, int alpha_mode, int memspace)
+{
+    return run_color(ctx, im, count, target, alpha_mode, memspace, true);
+}
+int pngb200_pack_batch(pngb200_ctx* ctx, pngb200_color_desc* im, size_t count, int target, int memspace)
+{
+    return run_color(ctx, im, count, target, PNGB200_ALPHA_ASIS, memspace, false);
+}
 }  // extern "C"
 
 // ---------------- encode stage 2: deflate ----------------

@@ -5,6 +5,9 @@ the reference's fixtures is committed here:
   pngsuite/*.png            the reference's PngSuite inputs (Sources/PNGIntegrationTests/Inputs/Common)
   invalid/*.png             its malformed inputs              (.../Inputs/Invalid)
   pngsuite_rgba.json        sha256 + size of each golden      (.../RGBA/<name>.png.rgba, RGBA16 LE)
+  ios/*.png                 the CgBI inputs (.../Inputs/iOS) and ios_rgba.json: sha256 of the same
+                            RGBA goldens after pixel.premultiplied(as: UInt8.self), which is what
+                            Roundtripping.swift:206-211 compares those inputs against
   gzip/*.gz                 the gzip fixtures                 (Sources/LZ77/docs.docc/GzipCompression)
   encode/*.png (+ .json)    a subset of the reference encoder's committed level-9 outputs
                             (Tests/Outputs) with the matching Tests/Baselines inputs, and
@@ -44,6 +47,20 @@ def main():
         raw = open(os.path.join(IT, "RGBA", f + ".rgba"), "rb").read()
         digests[f] = {"sha256": hashlib.sha256(raw).hexdigest(), "bytes": len(raw)}
     json.dump(digests, open(os.path.join(HERE, "pngsuite_rgba.json"), "w"), indent=0, sort_keys=True)
+    # iOS (CgBI) inputs: golden = RGBA<UInt16>.premultiplied(as: UInt8.self) of the common golden
+    # (PNG.RGBA.swift:141-155: shift 8, q = 257, premultiply on the high bytes, alpha requantised)
+    import numpy as np
+    os.makedirs(os.path.join(HERE, "ios"), exist_ok=True)
+    ios = {}
+    for f in sorted(os.listdir(os.path.join(IT, "Inputs/iOS"))):
+        shutil.copyfile(os.path.join(IT, "Inputs/iOS", f), os.path.join(HERE, "ios", f))
+        px = np.frombuffer(open(os.path.join(IT, "RGBA", f + ".rgba"), "rb").read(), dtype="<u2")
+        px = px.reshape(-1, 4).astype(np.uint32) >> 8
+        a = px[:, 3:4]
+        out = np.concatenate([(px[:, :3] * a + 127) // 255, a], axis=1) * 257
+        raw = out.astype("<u2").tobytes()
+        ios[f] = {"sha256": hashlib.sha256(raw).hexdigest(), "bytes": len(raw)}
+    json.dump(ios, open(os.path.join(HERE, "ios_rgba.json"), "w"), indent=0, sort_keys=True)
     gz = os.path.join(REF, "Sources", "LZ77", "docs.docc", "GzipCompression")
     os.makedirs(os.path.join(HERE, "gzip"), exist_ok=True)
     for f in sorted(os.listdir(gz)):

@@ -133,3 +133,22 @@ def unpack_rgba16(png: Png, storage: bytes) -> np.ndarray:
                 key = np.array(struct.unpack(">HHH", png.trns[:6]), dtype=np.uint32)
                 out[(v[:, :3] == key).all(axis=1), 3] = 0
     return out.astype(np.uint16)
+
+
+def format_fields(png: Png) -> dict:
+    """PNG.Format.recognize (Sources/PNG/Formats/PNG.Format.swift:161-330) reduced to what the
+    colour-target kernels need: sample order, chroma key in storage order, palette with tRNS merged."""
+    out = dict(color=png.color, depth=png.depth, bgr=png.cgbi and png.color in (2, 6), key=None, palette=None)
+    if png.color == 3:
+        pal = bytearray()
+        entries = [png.palette[i:i + 3] for i in range(0, len(png.palette), 3)]
+        alpha = list(png.trns or b"")
+        for i, e in enumerate(entries):
+            pal += bytes(e) + bytes([alpha[i] if i < len(alpha) else 255])
+        out["palette"] = bytes(pal)
+    elif png.trns is not None and png.color == 0:
+        out["key"] = struct.unpack(">H", png.trns[:2])
+    elif png.trns is not None and png.color == 2:
+        r, g, b = struct.unpack(">HHH", png.trns[:6])
+        out["key"] = (b, g, r) if png.cgbi else (r, g, b)
+    return out
