@@ -313,7 +313,7 @@ def main():
             hdescs[i].width, hdescs[i].height = w, h
             hdescs[i].volume, hdescs[i].depth = 8 * bpp, depth
             at += n
-        del d_pixels
+        del d_pixels, d_idat, descs
         torch.cuda.empty_cache()
         ctx.trim()  # the device-resident leg's arenas would otherwise sit beside the lanes'
 

@@ -149,6 +149,66 @@ int orc_unpack(const uint8_t* storage, size_t pixels, const orc_format* f, int t
  * PNG.Color.swift: colours missing from the palette map to entry 0) */
 int orc_pack(const void* pixels, size_t n, const orc_format* f, int target, uint8_t* storage);
 
+/* ---- PNG container ------------------------------------------------
+ * PNG.Image.decompress(stream:) / compress(stream:level:hint:) restated at file level
+ * (Sources/PNG/PNG.Image.swift:298-401, 576-670): signature, chunk framing and per-chunk CRC-32
+ * (Lexing/PNG.BytestreamSource.swift:17-83, PNG.BytestreamDestination.swift:66-95), IHDR / PLTE /
+ * tRNS parsing (Parsing/PNG.Header.swift:40-98, PNG.Palette.swift:27-55, PNG.Transparency.swift:68-122),
+ * the chunk-order rules that involve those chunks, IDAT concatenation.  Ancillary chunks other than
+ * PLTE / tRNS / bKGD are CRC-checked and otherwise ignored (metadata is outside the hot path). */
+enum {
+    /* PNG.LexingError (Lexing/PNG.LexingError.swift) */
+    ORC_ERR_LEX_TRUNCATED_SIGNATURE    = -80,
+    ORC_ERR_LEX_INVALID_SIGNATURE      = -81,
+    ORC_ERR_LEX_TRUNCATED_CHUNK_HEADER = -82,
+    ORC_ERR_LEX_TRUNCATED_CHUNK_BODY   = -83, /* a = expected bytes */
+    ORC_ERR_LEX_INVALID_CHUNK_TYPE     = -84, /* a = type code */
+    ORC_ERR_LEX_INVALID_CHUNK_CHECKSUM = -85, /* a = declared, b = computed */
+    /* PNG.ParsingError (Parsing/PNG.ParsingError.swift), the cases IHDR / PLTE / tRNS can raise */
+    ORC_ERR_PARSE_HEADER_CHUNK_LENGTH      = -96,  /* a = length */
+    ORC_ERR_PARSE_HEADER_PIXEL_FORMAT_CODE = -97,  /* a = depth code, b = colour code */
+    ORC_ERR_PARSE_HEADER_PIXEL_FORMAT      = -98,  /* pixel format not allowed by the ios standard */
+    ORC_ERR_PARSE_HEADER_COMPRESSION_CODE  = -99,  /* a = code */
+    ORC_ERR_PARSE_HEADER_FILTER_CODE       = -100, /* a = code */
+    ORC_ERR_PARSE_HEADER_INTERLACING_CODE  = -101, /* a = code */
+    ORC_ERR_PARSE_HEADER_SIZE              = -102, /* a = x, b = y */
+    ORC_ERR_PARSE_UNEXPECTED_PALETTE       = -103,
+    ORC_ERR_PARSE_PALETTE_CHUNK_LENGTH     = -104, /* a = length */
+    ORC_ERR_PARSE_PALETTE_COUNT            = -105, /* a = count, b = max */
+    ORC_ERR_PARSE_UNEXPECTED_TRANSPARENCY  = -106,
+    ORC_ERR_PARSE_TRANSPARENCY_CHUNK_LENGTH = -107, /* a = length, b = expected */
+    ORC_ERR_PARSE_TRANSPARENCY_SAMPLE      = -108, /* a = sample, b = max */
+    ORC_ERR_PARSE_TRANSPARENCY_COUNT       = -109, /* a = count, b = max */
+    /* PNG.DecodingError (Decoding/PNG.DecodingError.swift): a = chunk, b = the other chunk */
+    ORC_ERR_DECODE_REQUIRED_CHUNK   = -112,
+    ORC_ERR_DECODE_DUPLICATE_CHUNK  = -113,
+    ORC_ERR_DECODE_UNEXPECTED_CHUNK = -114
+};
+
+typedef struct {
+    int32_t    status;
+    uint32_t   a, b;
+    uint32_t   width, height;
+    uint8_t    depth, color, interlaced, standard; /* standard: 0 common, 1 ios (CgBI) */
+    orc_format format;                             /* format.palette points at palette_rgba */
+    uint8_t    palette_rgba[1024];
+    uint64_t   idat_bytes;                         /* concatenated IDAT payload */
+    uint32_t   idat_chunks, chunks;
+    orc_inflate_result inflate;                    /* orc_png_decompress only */
+} orc_png_info;
+
+/* lex + parse the whole file (every chunk's CRC included), no image data decoded */
+int orc_png_inspect(const uint8_t* file, size_t n, orc_png_info* info);
+/* PNG.Image.decompress(stream:): storage gets w*h*bpp bytes; errors in the order the reference's
+ * streaming loop would meet them */
+int orc_png_decompress(const uint8_t* file, size_t n, orc_png_info* info, uint8_t* storage, size_t cap);
+/* PNG.Image.compress(stream:level:hint:) for an image without metadata: signature, [CgBI], IHDR,
+ * [PLTE], [tRNS], IDAT chunks of `idat_chunk` bytes (65544 in the reference's committed outputs:
+ * 2 x the ManagedBuffer capacity DeflatorOut gets for hint 1 << 15), IEND.  Returns bytes written. */
+size_t orc_png_compress(const uint8_t* storage, uint32_t w, uint32_t h, const orc_format* f,
+                        int interlaced, int level, size_t idat_chunk, uint8_t* out, size_t cap);
+size_t orc_png_compress_bound(uint32_t w, uint32_t h, const orc_format* f, int interlaced, size_t idat_chunk);
+
 #ifdef __cplusplus
 }
 #endif

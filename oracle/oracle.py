@@ -69,6 +69,20 @@ def make_format(color, depth, bgr=False, key=None, palette=None) -> Format:
     return f
 
 
+ERR_LEX_TRUNCATED_SIGNATURE, ERR_LEX_INVALID_SIGNATURE, ERR_LEX_TRUNCATED_CHUNK_HEADER = -80, -81, -82
+ERR_LEX_TRUNCATED_CHUNK_BODY, ERR_LEX_INVALID_CHUNK_TYPE, ERR_LEX_INVALID_CHUNK_CHECKSUM = -83, -84, -85
+ERR_PARSE_HEADER_CHUNK_LENGTH, ERR_PARSE_HEADER_PIXEL_FORMAT_CODE, ERR_PARSE_HEADER_PIXEL_FORMAT = -96, -97, -98
+ERR_PARSE_HEADER_COMPRESSION_CODE, ERR_PARSE_HEADER_FILTER_CODE, ERR_PARSE_HEADER_INTERLACING_CODE = -99, -100, -101
+ERR_PARSE_HEADER_SIZE, ERR_PARSE_UNEXPECTED_PALETTE, ERR_PARSE_PALETTE_CHUNK_LENGTH = -102, -103, -104
+ERR_PARSE_PALETTE_COUNT, ERR_PARSE_UNEXPECTED_TRANSPARENCY, ERR_PARSE_TRANSPARENCY_CHUNK_LENGTH = -105, -106, -107
+ERR_PARSE_TRANSPARENCY_SAMPLE, ERR_PARSE_TRANSPARENCY_COUNT = -108, -109
+ERR_DECODE_REQUIRED_CHUNK, ERR_DECODE_DUPLICATE_CHUNK, ERR_DECODE_UNEXPECTED_CHUNK = -112, -113, -114
+
+
+def fourcc(name: str) -> int:
+    return int.from_bytes(name.encode("ascii"), "big")
+
+
 class InflateResult(C.Structure):
     _fields_ = [
         ("status", C.c_int32),
@@ -79,6 +93,25 @@ class InflateResult(C.Structure):
         ("checksum", C.c_uint32),
         ("blocks", C.c_uint32),
     ]
+
+
+class PngInfo(C.Structure):
+    """orc_png_info"""
+    _fields_ = [
+        ("status", C.c_int32), ("a", C.c_uint32), ("b", C.c_uint32),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("depth", C.c_uint8), ("color", C.c_uint8), ("interlaced", C.c_uint8), ("standard", C.c_uint8),
+        ("format", Format), ("palette_rgba", C.c_uint8 * 1024),
+        ("idat_bytes", C.c_uint64), ("idat_chunks", C.c_uint32), ("chunks", C.c_uint32),
+        ("inflate", InflateResult),
+    ]
+
+    def fields(self) -> dict:
+        """the PNG.Format fields as keyword arguments for make_format / the product's colour calls"""
+        f = self.format
+        return dict(color=f.color, depth=f.depth, bgr=bool(f.bgr),
+                    key=tuple(f.key[: 1 if f.color == 0 else 3]) if f.has_key else None,
+                    palette=bytes(self.palette_rgba[: 4 * f.palette_count]) if f.color == 3 else None)
 
 
 def build(force: bool = False) -> str:
@@ -144,6 +177,15 @@ def lib():
         L.orc_unpack.restype = C.c_int
         L.orc_pack.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(Format), C.c_int, C.c_void_p]
         L.orc_pack.restype = C.c_int
+        L.orc_png_inspect.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(PngInfo)]
+        L.orc_png_inspect.restype = C.c_int
+        L.orc_png_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(PngInfo), C.c_void_p, C.c_size_t]
+        L.orc_png_decompress.restype = C.c_int
+        L.orc_png_compress.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(Format), C.c_int, C.c_int,
+                                       C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_png_compress.restype = C.c_size_t
+        L.orc_png_compress_bound.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(Format), C.c_int, C.c_size_t]
+        L.orc_png_compress_bound.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -251,3 +293,31 @@ def premultiply(color: int, alpha: int, bits: int) -> int:
 
 def straighten(color: int, alpha: int, bits: int) -> int:
     return lib().orc_straighten(color, alpha, bits)
+
+
+def png_inspect(data: bytes) -> PngInfo:
+    """lex + parse a PNG file (every chunk CRC-checked), no image data decoded"""
+    info = PngInfo()
+    lib().orc_png_inspect(data, len(data), C.byref(info))
+    return info
+
+
+def png_decompress(data: bytes):
+    """PNG.Image.decompress(stream:).  Returns (PngInfo, storage bytes or None on error)."""
+    probe = png_inspect(data)
+    size = probe.width * probe.height * ((probe.depth * _CHANNELS.get(probe.color, 0) + 7) >> 3)
+    buf = C.create_string_buffer(max(size, 1))
+    info = PngInfo()
+    st = lib().orc_png_decompress(data, len(data), C.byref(info), buf, size)
+    return info, (buf.raw[:size] if st == 0 else None)
+
+
+def png_compress(storage: bytes, w: int, h: int, fmt: Format, interlaced: bool = False, level: int = 9,
+                 idat_chunk: int = 65544) -> bytes:
+    """PNG.Image.compress(stream:level:) of an image without metadata -> the PNG file"""
+    L = lib()
+    cap = L.orc_png_compress_bound(w, h, C.byref(fmt), int(interlaced), idat_chunk)
+    buf = C.create_string_buffer(cap)
+    n = L.orc_png_compress(storage, w, h, C.byref(fmt), int(interlaced), level, idat_chunk, buf, cap)
+    assert n != C.c_size_t(-1).value
+    return buf.raw[:n]

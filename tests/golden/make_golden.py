@@ -77,7 +77,9 @@ def main():
             continue
         payload = idat_of(os.path.join(outs, f))
         filtered = zlib.decompress(payload)
+        whole = open(os.path.join(outs, f), "rb").read()
         enc[f] = {"idat_sha256": hashlib.sha256(payload).hexdigest(), "idat_bytes": len(payload),
+                  "file_sha256": hashlib.sha256(whole).hexdigest(), "file_bytes": len(whole),
                   "filtered_sha256": hashlib.sha256(filtered).hexdigest(),
                   "filtered_bytes": len(filtered)}
         if f in keep:
