@@ -57,6 +57,32 @@ typedef enum pngb200_status {
     PNGB200_ERR_PNG_EXTRANEOUS_COMPRESSED_DATA   = -49,
     PNGB200_ERR_PNG_INCOMPLETE_DATASTREAM        = -50,
     PNGB200_ERR_PNG_PALETTE_INDEX                = -51, /* indexed pixel beyond the palette: the reference traps */
+    /* PNG.LexingError (Sources/PNG/Lexing/PNG.LexingError.swift), file-level entry points */
+    PNGB200_ERR_LEX_TRUNCATED_SIGNATURE          = -80,
+    PNGB200_ERR_LEX_INVALID_SIGNATURE            = -81, /* a,b = the eight bytes found */
+    PNGB200_ERR_LEX_TRUNCATED_CHUNK_HEADER       = -82,
+    PNGB200_ERR_LEX_TRUNCATED_CHUNK_BODY         = -83, /* a = expected bytes */
+    PNGB200_ERR_LEX_INVALID_CHUNK_TYPE           = -84, /* a = type code */
+    PNGB200_ERR_LEX_INVALID_CHUNK_CHECKSUM       = -85, /* a = declared, b = computed */
+    /* PNG.ParsingError (Sources/PNG/Parsing/PNG.ParsingError.swift): what IHDR / PLTE / tRNS can raise */
+    PNGB200_ERR_PARSE_HEADER_CHUNK_LENGTH        = -96,  /* a = length */
+    PNGB200_ERR_PARSE_HEADER_PIXEL_FORMAT_CODE   = -97,  /* a = depth code, b = colour code */
+    PNGB200_ERR_PARSE_HEADER_PIXEL_FORMAT        = -98,  /* not allowed by the ios standard */
+    PNGB200_ERR_PARSE_HEADER_COMPRESSION_CODE    = -99,  /* a = code */
+    PNGB200_ERR_PARSE_HEADER_FILTER_CODE         = -100, /* a = code */
+    PNGB200_ERR_PARSE_HEADER_INTERLACING_CODE    = -101, /* a = code */
+    PNGB200_ERR_PARSE_HEADER_SIZE                = -102, /* a = x, b = y */
+    PNGB200_ERR_PARSE_UNEXPECTED_PALETTE         = -103,
+    PNGB200_ERR_PARSE_PALETTE_CHUNK_LENGTH       = -104, /* a = length */
+    PNGB200_ERR_PARSE_PALETTE_COUNT              = -105, /* a = count, b = max */
+    PNGB200_ERR_PARSE_UNEXPECTED_TRANSPARENCY    = -106,
+    PNGB200_ERR_PARSE_TRANSPARENCY_CHUNK_LENGTH  = -107, /* a = length, b = expected */
+    PNGB200_ERR_PARSE_TRANSPARENCY_SAMPLE        = -108, /* a = sample, b = max */
+    PNGB200_ERR_PARSE_TRANSPARENCY_COUNT         = -109, /* a = count, b = max */
+    /* PNG.DecodingError (Sources/PNG/Decoding/PNG.DecodingError.swift): a = chunk, b = the other chunk */
+    PNGB200_ERR_DECODE_REQUIRED_CHUNK            = -112,
+    PNGB200_ERR_DECODE_DUPLICATE_CHUNK           = -113,
+    PNGB200_ERR_DECODE_UNEXPECTED_CHUNK          = -114,
     /* API-level */
     PNGB200_ERR_OUTPUT_CAPACITY                  = -64,
     PNGB200_ERR_BAD_ARGUMENT                     = -65,
@@ -249,6 +275,57 @@ typedef struct pngb200_encode_desc {
 } pngb200_encode_desc;
 
 int pngb200_encode_batch(pngb200_ctx* ctx, pngb200_encode_desc* images, size_t count, int memspace);
+
+/* ---- whole PNG files ------------------------------------------------
+ * PNG.Image.decompress(stream:) and PNG.Image.compress(stream:level:hint:) at file level
+ * (Sources/PNG/PNG.Image.swift:298-401, 576-670): signature, chunk framing, per-chunk CRC-32
+ * (Lexing/PNG.BytestreamSource.swift:17-83, PNG.BytestreamDestination.swift:66-95), IHDR / PLTE / tRNS,
+ * the ordering rules that involve them, IDAT concatenation and framing.  The host reads chunk HEADERS
+ * only; CRC-32 of every chunk, IDAT gather / scatter and the codec run on the device.  Ancillary chunks
+ * other than PLTE / tRNS / bKGD are CRC-checked and otherwise ignored (metadata is not on the hot path).
+ * Errors come back in the order the reference's streaming loop meets them. */
+typedef struct pngb200_png_desc {
+    const uint8_t*       file;          /* in: the PNG file, HOST memory */
+    size_t               file_len;
+    void*                pixels;        /* out: PNG.Image.storage (memspace of the call) */
+    size_t               pixels_cap;    /* >= storage_size (pngb200_png_inspect_batch reports it) */
+    /* out: PNG.Header + PNG.Layout.format */
+    uint32_t             width, height;
+    uint8_t              depth, color, interlaced, standard; /* standard: 0 common, 1 ios (CgBI) */
+    pngb200_pixel_format format;        /* ready for pngb200_unpack_batch; palette -> palette_rgba */
+    uint8_t              palette_rgba[1024];
+    uint64_t             storage_size;  /* width * height * bytes per pixel */
+    uint64_t             idat_bytes;    /* concatenated IDAT payload */
+    uint32_t             idat_chunks, chunks;
+    int32_t              status;        /* pngb200_status */
+    uint32_t             err_a, err_b;
+    uint32_t             checksum, blocks;
+    uint64_t             produced;
+} pngb200_png_desc;
+/* host only: walk the chunk headers, parse IHDR / PLTE / tRNS, fill the out fields (no CRC check, no
+ * GPU) -- what a caller needs to size `pixels` */
+int pngb200_png_inspect_batch(pngb200_png_desc* files, size_t count);
+/* `memspace` is where `pixels` live; files are always host memory */
+int pngb200_png_decode_batch(pngb200_ctx* ctx, pngb200_png_desc* files, size_t count, int memspace);
+
+typedef struct pngb200_png_encode_desc {
+    const void*          pixels;        /* in: PNG.Image.storage (memspace of the call) */
+    size_t               pixels_len;
+    uint32_t             width, height;
+    pngb200_pixel_format format;        /* bgr = 1 writes the ios standard (CgBI chunk, raw deflate) */
+    uint8_t              interlaced;
+    int32_t              level;         /* 0...13 */
+    uint32_t             idat_chunk;    /* bytes per IDAT chunk; 0 = 65544, what the reference emits for its
+                                           default hint (2 x the capacity malloc gives DeflatorOut's buffer) */
+    uint8_t*             file;          /* out: the PNG file, HOST memory */
+    size_t               file_cap;      /* >= pngb200_png_encode_bound(...) */
+    int32_t              status;
+    uint32_t             checksum, blocks;
+    uint64_t             produced;      /* file bytes */
+} pngb200_png_encode_desc;
+size_t pngb200_png_encode_bound(uint32_t width, uint32_t height, const pngb200_pixel_format* format, int interlaced,
+                                uint32_t idat_chunk);
+int    pngb200_png_encode_batch(pngb200_ctx* ctx, pngb200_png_encode_desc* images, size_t count, int memspace);
 
 /* size helpers (host arithmetic only) */
 size_t pngb200_filtered_size(uint32_t width, uint32_t height, int volume, int interlaced);

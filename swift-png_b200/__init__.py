@@ -48,6 +48,14 @@ ERR_GZIP_HEADER_CHECKSUM_UNSUPPORTED = -35
 ERR_PNG_EXTRANEOUS_IMAGE_DATA = -48
 ERR_PNG_EXTRANEOUS_COMPRESSED_DATA = -49
 ERR_PNG_INCOMPLETE_DATASTREAM = -50
+ERR_LEX_TRUNCATED_SIGNATURE, ERR_LEX_INVALID_SIGNATURE, ERR_LEX_TRUNCATED_CHUNK_HEADER = -80, -81, -82
+ERR_LEX_TRUNCATED_CHUNK_BODY, ERR_LEX_INVALID_CHUNK_TYPE, ERR_LEX_INVALID_CHUNK_CHECKSUM = -83, -84, -85
+ERR_PARSE_HEADER_CHUNK_LENGTH, ERR_PARSE_HEADER_PIXEL_FORMAT_CODE, ERR_PARSE_HEADER_PIXEL_FORMAT = -96, -97, -98
+ERR_PARSE_HEADER_COMPRESSION_CODE, ERR_PARSE_HEADER_FILTER_CODE, ERR_PARSE_HEADER_INTERLACING_CODE = -99, -100, -101
+ERR_PARSE_HEADER_SIZE, ERR_PARSE_UNEXPECTED_PALETTE, ERR_PARSE_PALETTE_CHUNK_LENGTH = -102, -103, -104
+ERR_PARSE_PALETTE_COUNT, ERR_PARSE_UNEXPECTED_TRANSPARENCY, ERR_PARSE_TRANSPARENCY_CHUNK_LENGTH = -105, -106, -107
+ERR_PARSE_TRANSPARENCY_SAMPLE, ERR_PARSE_TRANSPARENCY_COUNT = -108, -109
+ERR_DECODE_REQUIRED_CHUNK, ERR_DECODE_DUPLICATE_CHUNK, ERR_DECODE_UNEXPECTED_CHUNK = -112, -113, -114
 ERR_OUTPUT_CAPACITY = -64
 ERR_BAD_ARGUMENT = -65
 ERR_CUDA = -66
@@ -134,6 +142,29 @@ class ColorDesc(C.Structure):
     ]
 
 
+class PngDesc(C.Structure):
+    """pngb200_png_desc"""
+    _fields_ = [
+        ("file", C.c_void_p), ("file_len", C.c_size_t), ("pixels", C.c_void_p), ("pixels_cap", C.c_size_t),
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("depth", C.c_uint8), ("color", C.c_uint8), ("interlaced", C.c_uint8), ("standard", C.c_uint8),
+        ("format", PixelFormat), ("palette_rgba", C.c_uint8 * 1024),
+        ("storage_size", C.c_uint64), ("idat_bytes", C.c_uint64), ("idat_chunks", C.c_uint32), ("chunks", C.c_uint32),
+        ("status", C.c_int32), ("err_a", C.c_uint32), ("err_b", C.c_uint32),
+        ("checksum", C.c_uint32), ("blocks", C.c_uint32), ("produced", C.c_uint64),
+    ]
+
+
+class PngEncodeDesc(C.Structure):
+    """pngb200_png_encode_desc"""
+    _fields_ = [
+        ("pixels", C.c_void_p), ("pixels_len", C.c_size_t), ("width", C.c_uint32), ("height", C.c_uint32),
+        ("format", PixelFormat), ("interlaced", C.c_uint8), ("level", C.c_int32), ("idat_chunk", C.c_uint32),
+        ("file", C.c_void_p), ("file_cap", C.c_size_t),
+        ("status", C.c_int32), ("checksum", C.c_uint32), ("blocks", C.c_uint32), ("produced", C.c_uint64),
+    ]
+
+
 class PNGB200Error(RuntimeError):
     def __init__(self, status: int, message: str = ""):
         super().__init__(f"pngb200 status {status}: {message}")
@@ -168,6 +199,14 @@ def lib():
     L.pngb200_unpack_batch.restype = C.c_int
     L.pngb200_pack_batch.argtypes = [C.c_void_p, C.POINTER(ColorDesc), C.c_size_t, C.c_int, C.c_int]
     L.pngb200_pack_batch.restype = C.c_int
+    L.pngb200_png_inspect_batch.argtypes = [C.POINTER(PngDesc), C.c_size_t]
+    L.pngb200_png_inspect_batch.restype = C.c_int
+    L.pngb200_png_decode_batch.argtypes = [C.c_void_p, C.POINTER(PngDesc), C.c_size_t, C.c_int]
+    L.pngb200_png_decode_batch.restype = C.c_int
+    L.pngb200_png_encode_bound.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(PixelFormat), C.c_int, C.c_uint32]
+    L.pngb200_png_encode_bound.restype = C.c_size_t
+    L.pngb200_png_encode_batch.argtypes = [C.c_void_p, C.POINTER(PngEncodeDesc), C.c_size_t, C.c_int]
+    L.pngb200_png_encode_batch.restype = C.c_int
     L.pngb200_ctx_trim.argtypes = [C.c_void_p]
     L.pngb200_ctx_trim.restype = C.c_int
     L.pngb200_last_error.argtypes = [C.c_void_p]
@@ -463,6 +502,84 @@ def pack_batch(ctx: Context, images, target: int = TARGET_RGBA8):
         _fill_format(descs[i].format, keep, g["color"], g["depth"], g.get("bgr"), g.get("key"), g.get("palette"))
     ctx.check(ctx._lib.pngb200_pack_batch(ctx.handle, descs, n, target, MEM_HOST))
     return [k[1].raw[: k[2]] for k in keep if isinstance(k, tuple)]
+
+
+class PngImage:
+    """What PNG.Image.decompress(stream:) returns, as far as the hot path goes: status (+ the Swift
+    error's associated values), header, PNG.Format fields (`fields`, ready for unpack_batch) and storage."""
+
+    def __init__(self, d: PngDesc, storage):
+        self.status, self.err_a, self.err_b = d.status, d.err_a, d.err_b
+        self.width, self.height, self.depth, self.color = d.width, d.height, d.depth, d.color
+        self.interlaced, self.standard = bool(d.interlaced), d.standard
+        self.idat_bytes, self.idat_chunks, self.chunks = d.idat_bytes, d.idat_chunks, d.chunks
+        self.checksum, self.blocks, self.produced = d.checksum, d.blocks, d.produced
+        f = d.format
+        self.fields = dict(color=f.color, depth=f.depth, bgr=bool(f.bgr),
+                           key=tuple(f.key[: 1 if f.color == 0 else 3]) if f.has_key else None,
+                           palette=bytes(d.palette_rgba[: 4 * f.palette_count]) if f.color == 3 else None)
+        self.storage = storage
+
+
+def _png_descs(files):
+    files = [bytes(f) for f in files]
+    descs = (PngDesc * max(len(files), 1))()
+    keep = []
+    for i, f in enumerate(files):
+        src = C.create_string_buffer(f, len(f)) if f else C.create_string_buffer(1)
+        keep.append(src)
+        descs[i].file, descs[i].file_len = _buf_addr(src), len(f)
+    return files, descs, keep
+
+
+def png_inspect(files):
+    """pngb200_png_inspect_batch: header walk only (no CRC check, no GPU).  Returns [PngImage]."""
+    files, descs, keep = _png_descs(files)
+    rc = lib().pngb200_png_inspect_batch(descs, len(files))
+    if rc != OK:
+        raise PNGB200Error(rc, "png_inspect")
+    return [PngImage(descs[i], None) for i in range(len(files))]
+
+
+def png_decode_batch(ctx: Context, files):
+    """PNG.Image.decompress(stream:) over a batch of PNG files (bytes).  Returns [PngImage]."""
+    files, descs, keep = _png_descs(files)
+    n = len(files)
+    rc = ctx._lib.pngb200_png_inspect_batch(descs, n)
+    if rc != OK:
+        raise PNGB200Error(rc, "png_inspect")
+    outs = []
+    for i in range(n):
+        dst = C.create_string_buffer(max(int(descs[i].storage_size), 1))
+        outs.append(dst)
+        descs[i].pixels, descs[i].pixels_cap = _buf_addr(dst), int(descs[i].storage_size)
+    ctx.check(ctx._lib.pngb200_png_decode_batch(ctx.handle, descs, n, MEM_HOST))
+    return [PngImage(descs[i], outs[i].raw[: descs[i].storage_size] if descs[i].status == OK else None) for i in range(n)]
+
+
+def png_encode_batch(ctx: Context, images, level: int = 9, idat_chunk: int = 0):
+    """PNG.Image.compress(stream:level:) over a batch.  images: dicts with storage, width, height,
+    [interlaced] and the PNG.Format fields.  Returns [(status, file bytes)]."""
+    images = list(images)
+    n = len(images)
+    descs = (PngEncodeDesc * max(n, 1))()
+    keep = []
+    for i, g in enumerate(images):
+        st = bytes(g["storage"])
+        src = C.create_string_buffer(st, len(st))
+        _fill_format(descs[i].format, keep, g["color"], g["depth"], g.get("bgr"), g.get("key"), g.get("palette"))
+        il = int(bool(g.get("interlaced", False)))
+        cap = ctx._lib.pngb200_png_encode_bound(g["width"], g["height"], C.byref(descs[i].format), il, idat_chunk)
+        dst = C.create_string_buffer(cap)
+        keep.append((src, dst))
+        descs[i].pixels, descs[i].pixels_len = _buf_addr(src), len(st)
+        descs[i].width, descs[i].height, descs[i].interlaced = g["width"], g["height"], il
+        descs[i].level = level if isinstance(level, int) else level[i]
+        descs[i].idat_chunk = idat_chunk
+        descs[i].file, descs[i].file_cap = _buf_addr(dst), cap
+    ctx.check(ctx._lib.pngb200_png_encode_batch(ctx.handle, descs, n, MEM_HOST))
+    pairs = [k for k in keep if isinstance(k, tuple)]
+    return [(descs[i].status, pairs[i][1].raw[: descs[i].produced]) for i in range(n)]
 
 
 def deflate_batch(ctx: Context, streams, level: int = 9, fmt: int = FORMAT_ZLIB, exponent: int = 15):

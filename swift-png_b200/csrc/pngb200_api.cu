@@ -18,6 +18,7 @@
 #include "deflate.cuh"
 #include "filter.cuh"
 #include "color.cuh"
+#include "crc32.cuh"
 #include "inflate_parallel.cuh"
 #include "inflate_serial.cuh"
 #include "unfilter.cuh"
@@ -95,9 +96,10 @@ struct pngb200_ctx {
     bool         pending = false;
     int          pending_memspace = 0;
     // device workspaces (grow-only)
-    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order, d_scratch, d_dfscratch, d_dfjobs, d_dfres, d_enc;
+    DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order, d_scratch, d_dfscratch, d_dfjobs, d_dfres, d_enc,
+           d_file, d_crc, d_seg, d_crctab;
     // pinned host tables
-    PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order;
+    PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order, h_crc, h_seg;
     uint64_t scratch_stride = 0;       // layout of d_scratch the last inflate launch used
     size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // decode stage boundaries
@@ -348,6 +350,67 @@ int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
     return PNGB200_OK;
 }
 
+
+// Host-memory batches with a lot of bytes to move are cut into chunks that four lanes (helper
+// contexts on the same GPU, one host thread each) work through round-robin, so that one chunk's
+// H2D / D2H copies overlap another chunk's kernels.  Results are identical: images are
+// independent units.  Chunk size is a trade: the inflate kernel runs one CTA per stream, so small
+// chunks leave SMs idle, while few chunks leave nothing to overlap.  Measured on B200 (r01,
+// GPixels/s end to end, lanes x chunks per lane): 444 x 8K RGBA8 4x1 7.1, 3x1 6.9, 2x1 6.4, 4x2 5.9,
+// 4x4 4.1; 1184 x 1080p 4x2 8.8, 3x2 8.0, 4x3 8.2, 4x4 7.2, 4x1 5.7, 1x1 5.6 -- i.e. about one stream
+// per SM in every chunk, chunk count a multiple of the lane count.
+// `bytes_of(i)`: bytes item i moves over PCIe; `work(lane, lo, n)`: process items [lo, lo + n) on `lane`.
+template <typename BytesOf, typename Work>
+int run_over_lanes(pngb200_ctx* ctx, size_t count, int memspace, BytesOf bytes_of, Work work)
+{
+    size_t bytes = 0;
+    for (size_t i = 0; i < count; ++i) bytes += bytes_of(i);
+    // tunable for experiments: PNGB200_LANES, PNGB200_CHUNKS_PER_LANE (0 / unset = the rule above)
+    const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 4;
+    const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(0, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 0;
+    constexpr size_t kMinChunk = 32;
+    if (memspace != PNGB200_MEM_HOST || count < 2 * kMinChunk || bytes < ((size_t)256 << 20)) return work(ctx, 0, count);
+    while (ctx->lanes.size() < kLanes) {
+        pngb200_ctx* lane = pngb200_ctx_create(ctx->device);
+        if (!lane) return set_error(ctx, PNGB200_ERR_CUDA, "cannot create a pipeline lane: %s", g_last_error.c_str());
+        ctx->lanes.push_back(lane);
+    }
+    size_t nchunks;
+    if (kPerLane) {
+        nchunks = kPerLane * kLanes;
+    } else {
+        nchunks = std::max<size_t>(1, count / (size_t)ctx->sm_count);
+        nchunks = (nchunks + kLanes - 1) / kLanes * kLanes;
+    }
+    nchunks = std::max<size_t>(1, std::min(nchunks, count / kMinChunk));
+    std::vector<size_t> cut(nchunks + 1);  // chunk boundaries balanced by bytes
+    {
+        size_t acc = 0, k = 1;
+        cut[0] = 0;
+        for (size_t i = 0; i < count && k < nchunks; ++i) {
+            acc += bytes_of(i);
+            if (acc * nchunks >= bytes * k) cut[k++] = i + 1;
+        }
+        while (k <= nchunks) cut[k++] = count;
+    }
+    std::vector<int> rcs(kLanes, PNGB200_OK);
+    std::vector<std::thread> workers;
+    for (size_t l = 0; l < kLanes; ++l)
+        workers.emplace_back([&, l]() {
+            pngb200_ctx* lane = ctx->lanes[l];
+            lane->inflate_mode = ctx->inflate_mode;
+            for (size_t c = l; c < nchunks; c += kLanes) {
+                size_t lo = cut[c], n = cut[c + 1] - cut[c];
+                if (n == 0) continue;
+                int rc = work(lane, lo, n);
+                if (rc != PNGB200_OK) { rcs[l] = rc; ctx->error = lane->error; return; }
+            }
+        });
+    for (std::thread& t : workers) t.join();
+    for (int rc : rcs)
+        if (rc != PNGB200_OK) return rc;
+    return PNGB200_OK;
+}
 }  // namespace
 
 // ================================ C ABI ================================
@@ -424,9 +487,9 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->d_jobs, &ctx->d_results, &ctx->d_imgjobs, &ctx->d_genjobs, &ctx->d_misc,
                       &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_order, &ctx->d_scratch, &ctx->d_dfscratch,
-                      &ctx->d_dfjobs, &ctx->d_dfres, &ctx->d_enc})
+                      &ctx->d_dfjobs, &ctx->d_dfres, &ctx->d_enc, &ctx->d_file, &ctx->d_crc, &ctx->d_seg, &ctx->d_crctab})
         b->release();
-    for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order})
+    for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order, &ctx->h_crc, &ctx->h_seg})
         b->release();
     for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -440,7 +503,7 @@ int pngb200_ctx_trim(pngb200_ctx* ctx)
     for (pngb200_ctx* lane : ctx->lanes) pngb200_ctx_trim(lane);
     DeviceGuard guard(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
-    for (DevBuf* b : {&ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_scratch, &ctx->d_dfscratch, &ctx->d_enc})
+    for (DevBuf* b : {&ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_scratch, &ctx->d_dfscratch, &ctx->d_enc, &ctx->d_file})
         b->release();
     ctx->scratch_stride = 0;
     return PNGB200_OK;
@@ -663,58 +726,12 @@ int pngb200_decode_batch_finish(pngb200_ctx* ctx, pngb200_image_desc* im, size_t
 int pngb200_decode_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)
 {
     if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
-    // Host-memory batches with a lot of bytes to move are cut into chunks that four lanes (helper
-    // contexts on the same GPU, one host thread each; measured r01: 1/3/4/6 lanes = 5.6/6.8/7.1/6.6
-    // GPixels/s end to end on 1184 x 1080p) work through round-robin, so that one chunk's
-    // H2D / D2H copies overlap another chunk's kernels.  Results are identical: images are
-    // independent units.
-    size_t bytes = 0;
-    for (size_t i = 0; i < count; ++i)
-        bytes += im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume);
-    // lanes / chunks per lane: tunable for experiments (PNGB200_LANES, PNGB200_CHUNKS_PER_LANE)
-    const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 4;
-    const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(1, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 4;
-    constexpr size_t kMinChunk = 32;
-    if (memspace != PNGB200_MEM_HOST || count < 2 * kMinChunk || bytes < ((size_t)256 << 20)) {
-        int rc = pngb200_decode_batch_enqueue(ctx, im, count, memspace);
-        if (rc != PNGB200_OK) return rc;
-        return pngb200_decode_batch_finish(ctx, im, count);
-    }
-    while (ctx->lanes.size() < kLanes) {
-        pngb200_ctx* lane = pngb200_ctx_create(ctx->device);
-        if (!lane) return set_error(ctx, PNGB200_ERR_CUDA, "cannot create a pipeline lane: %s", g_last_error.c_str());
-        lane->inflate_mode = ctx->inflate_mode;
-        ctx->lanes.push_back(lane);
-    }
-    const size_t nchunks = std::min<size_t>(count / kMinChunk, kPerLane * kLanes);
-    std::vector<size_t> cut(nchunks + 1);  // chunk boundaries balanced by bytes
-    {
-        size_t acc = 0, k = 1;
-        cut[0] = 0;
-        for (size_t i = 0; i < count && k < nchunks; ++i) {
-            acc += im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume);
-            if (acc * nchunks >= bytes * k) cut[k++] = i + 1;
-        }
-        while (k <= nchunks) cut[k++] = count;
-    }
-    std::vector<int> rcs(kLanes, PNGB200_OK);
-    std::vector<std::thread> workers;
-    for (size_t l = 0; l < kLanes; ++l)
-        workers.emplace_back([&, l]() {
-            pngb200_ctx* lane = ctx->lanes[l];
-            lane->inflate_mode = ctx->inflate_mode;
-            for (size_t c = l; c < nchunks; c += kLanes) {
-                size_t lo = cut[c], n = cut[c + 1] - cut[c];
-                if (n == 0) continue;
-                int rc = pngb200_decode_batch_enqueue(lane, im + lo, n, PNGB200_MEM_HOST);
-                if (rc == PNGB200_OK) rc = pngb200_decode_batch_finish(lane, im + lo, n);
-                if (rc != PNGB200_OK) { rcs[l] = rc; ctx->error = lane->error; return; }
-            }
-        });
-    for (std::thread& t : workers) t.join();
-    for (int rc : rcs)
-        if (rc != PNGB200_OK) return rc;
-    return PNGB200_OK;
+    return run_over_lanes(ctx, count, memspace,
+                          [&](size_t i) { return im[i].idat_len + pngb200_storage_size(im[i].width, im[i].height, im[i].volume); },
+                          [&](pngb200_ctx* lane, size_t lo, size_t n) {
+                              int rc = pngb200_decode_batch_enqueue(lane, im + lo, n, memspace);
+                              return rc != PNGB200_OK ? rc : pngb200_decode_batch_finish(lane, im + lo, n);
+                          });
 }
 
 int pngb200_unfilter_batch(pngb200_ctx* ctx, pngb200_image_desc* im, size_t count, int memspace)
@@ -1271,3 +1288,5 @@ void pngb200_inflator_error(const pngb200_inflator* z, int* status, uint32_t* a,
 }
 
 }  // extern "C"
+
+#include "png_file.cuh"

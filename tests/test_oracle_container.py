@@ -10,6 +10,7 @@ import zlib
 
 import pytest
 
+import container_cases as cc
 import pngio
 from conftest import GOLDEN, REFERENCE
 
@@ -86,62 +87,25 @@ def test_level9_all_28_outputs_whole_file(orc):
         assert len(got) == ENC[name]["file_bytes"] and hashlib.sha256(got).hexdigest() == ENC[name]["file_sha256"], name
 
 
-def _chunk(typ, body, crc=None):
-    return struct.pack(">I", len(body)) + typ + body + struct.pack(">I", zlib.crc32(typ + body) if crc is None else crc)
-
-
-def _png(chunks):
-    return pngio.SIGNATURE + b"".join(chunks)
-
-
 def test_lexing_and_ordering_rules(orc):
     o = orc
-    ihdr = _chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 3, 0, 0, 0))
-    gray = _chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 0, 0, 0, 0))
-    idat = _chunk(b"IDAT", zlib.compress(bytes([0, 0, 1, 0, 1, 0])))
-    plte = _chunk(b"PLTE", bytes(range(6)))
-    iend = _chunk(b"IEND", b"")
+    _chunk, _png = cc.chunk, cc.png
+    ihdr, plte, idat, iend = cc.IHDR, cc.PLTE, cc.IDAT, cc.IEND
     ok = _png([ihdr, plte, _chunk(b"tRNS", b"\x80"), idat, iend])
     info, storage = o.png_decompress(ok)
     assert info.status == 0 and storage == bytes([0, 1, 1, 0])
     assert info.fields()["palette"] == bytes([0, 1, 2, 0x80, 3, 4, 5, 255])
-    cases = [
-        (b"\x89PNG", (o.ERR_LEX_TRUNCATED_SIGNATURE,)),
-        (pngio.SIGNATURE + b"\0\0\0", (o.ERR_LEX_TRUNCATED_CHUNK_HEADER,)),
-        (_png([ihdr])[:-3], (o.ERR_LEX_TRUNCATED_CHUNK_BODY, 17)),
-        (_png([_chunk(b"IH\x7fR", b"")]), (o.ERR_LEX_INVALID_CHUNK_TYPE, int.from_bytes(b"IH\x7fR", "big"))),
-        (_png([_chunk(b"abCd", b""), ihdr]), (o.ERR_DECODE_REQUIRED_CHUNK, o.fourcc("IHDR"), o.fourcc("abCd"))),
-        (_png([_chunk(b"aBcD", b"")]), (o.ERR_LEX_INVALID_CHUNK_TYPE,)),  # reserved bit set
-        (_png([plte, ihdr]), (o.ERR_DECODE_REQUIRED_CHUNK, o.fourcc("IHDR"), o.fourcc("PLTE"))),
-        (_png([ihdr, ihdr]), (o.ERR_DECODE_DUPLICATE_CHUNK, o.fourcc("IHDR"))),
-        (_png([ihdr, plte, plte]), (o.ERR_DECODE_DUPLICATE_CHUNK, o.fourcc("PLTE"))),
-        (_png([ihdr, idat, iend]), (o.ERR_DECODE_REQUIRED_CHUNK, o.fourcc("PLTE"), o.fourcc("IDAT"))),
-        (_png([ihdr, _chunk(b"tRNS", b"\1"), plte]), (o.ERR_DECODE_REQUIRED_CHUNK, o.fourcc("PLTE"), o.fourcc("tRNS"))),
-        (_png([ihdr, plte, _chunk(b"tRNS", b"\1\2\3")]), (o.ERR_PARSE_TRANSPARENCY_COUNT, 3, 2)),
-        (_png([ihdr, _chunk(b"PLTE", bytes(7))]), (o.ERR_PARSE_PALETTE_CHUNK_LENGTH, 7)),
-        (_png([ihdr, _chunk(b"PLTE", bytes(3 * 257))]), (o.ERR_PARSE_PALETTE_COUNT, 257, 256)),
-        (_png([gray, plte]), (o.ERR_PARSE_UNEXPECTED_PALETTE,)),
-        (_png([gray, _chunk(b"tRNS", b"\1")]), (o.ERR_PARSE_TRANSPARENCY_CHUNK_LENGTH, 1, 2)),
-        (_png([gray, _chunk(b"tRNS", b"\1\0")]), (o.ERR_PARSE_TRANSPARENCY_SAMPLE, 256, 255)),
-        (_png([ihdr, plte, _chunk(b"gAMA", bytes(4))]), (o.ERR_DECODE_UNEXPECTED_CHUNK, o.fourcc("gAMA"), o.fourcc("PLTE"))),
-        (_png([ihdr, plte, idat, plte]), (o.ERR_DECODE_UNEXPECTED_CHUNK, o.fourcc("PLTE"), o.fourcc("IDAT"))),
-        (_png([ihdr, plte, idat, _chunk(b"tEXt", b"k\0v"), idat, iend]), (o.ERR_DECODE_UNEXPECTED_CHUNK, o.fourcc("IDAT"), o.fourcc("IDAT"))),
-        (_png([ihdr, plte, idat]), (o.ERR_LEX_TRUNCATED_CHUNK_HEADER,)),
-        (_png([_chunk(b"IHDR", bytes(12))]), (o.ERR_PARSE_HEADER_CHUNK_LENGTH, 12)),
-        (_png([_chunk(b"IHDR", struct.pack(">IIBBBBB", 0, 2, 8, 0, 0, 0, 0))]), (o.ERR_PARSE_HEADER_SIZE, 0, 2)),
-        (_png([_chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 0, 1, 0, 0))]), (o.ERR_PARSE_HEADER_COMPRESSION_CODE, 1)),
-        (_png([_chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 0, 0, 2, 0))]), (o.ERR_PARSE_HEADER_FILTER_CODE, 2)),
-        (_png([_chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 0, 0, 0, 2))]), (o.ERR_PARSE_HEADER_INTERLACING_CODE, 2)),
-        (_png([_chunk(b"CgBI", bytes(4)), gray]), (o.ERR_PARSE_HEADER_PIXEL_FORMAT,)),
-    ]
+    cases = cc.structural_cases(o)
     for data, want in cases:
         for info in (o.png_inspect(data), o.png_decompress(data)[0]):
             got = (info.status, info.a, info.b)
             assert got[: len(want)] == want, (data[:40], got, want)
     # decoder errors keep their place in stream order: bad deflate data in the first IDAT wins over a
     # CRC error in a later chunk; a CRC error in the IDAT itself wins over its contents
-    bad = _chunk(b"IDAT", b"\x78\x9c\x07")
-    later = _chunk(b"tEXt", b"k\0v", crc=1)
+    _chunk, _png = cc.chunk, cc.png
+    ihdr, plte, iend = cc.IHDR, cc.PLTE, cc.IEND
+    bad = cc.chunk(b"IDAT", b"\x78\x9c\x07")
+    later = cc.chunk(b"tEXt", b"k\0v", crc=1)
     info, _ = o.png_decompress(_png([ihdr, plte, bad, later, iend]))
     assert info.status == o.ERR_BLOCK_TYPE
     assert o.png_inspect(_png([ihdr, plte, bad, later, iend])).status == o.ERR_LEX_INVALID_CHUNK_CHECKSUM
