@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: whole batch if <= 110 GB pinned)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-api", choices=["idat", "files"], default="idat",
+                    help="host leg through pngb200_decode_batch (IDAT payloads) or pngb200_png_decode_batch (whole PNG files, "
+                         "65544-byte IDAT chunks: chunk CRC-32 and IDAT gather on the device)")
     ap.add_argument("--e2e-sweep", default="", help="experiment: comma list of LANESxCHUNKS_PER_LANE to time the host leg with")
     ap.add_argument("--cpu-images", type=int, default=0)
     return ap.parse_args()
@@ -297,28 +300,47 @@ def main():
         while EB > 8 and EB * per_image * 2.5 * max(world, 1) > avail:
             EB //= 2  # pinned host staging for the whole batch must fit comfortably in host RAM
         full_B, B = B, EB
-        comp_total = sum(len(items[i % len(items)]["idat"]) for i in range(B))
+        if args.e2e_api == "files":
+            import struct
+            import zlib
+
+            def chunk(t, body):
+                return struct.pack(">I", len(body)) + t + body + struct.pack(">I", zlib.crc32(t + body))
+
+            for it in items:  # the file the reference's encoder would frame around this IDAT payload
+                z = it["idat"]
+                it["file"] = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, 6, 0, 0, 0)) +
+                              b"".join(chunk(b"IDAT", z[o:o + 65544]) for o in range(0, len(z), 65544)) + chunk(b"IEND", b""))
+        src_key = "file" if args.e2e_api == "files" else "idat"
+        comp_total = sum(len(items[i % len(items)][src_key]) for i in range(B))
         h_in = torch.empty(comp_total, dtype=torch.uint8).pin_memory()
         h_out = torch.empty((B, storage_bytes), dtype=torch.uint8).pin_memory()
-        hdescs = (pkg.ImageDesc * B)()
+        hdescs = (pkg.PngDesc * B)() if args.e2e_api == "files" else (pkg.ImageDesc * B)()
         at = 0
         for i in range(B):
             it = items[i % len(items)]
-            n = len(it["idat"])
-            h_in[at:at + n] = torch.frombuffer(bytearray(it["idat"]), dtype=torch.uint8)
-            hdescs[i].idat = h_in.data_ptr() + at
-            hdescs[i].idat_len = n
+            n = len(it[src_key])
+            h_in[at:at + n] = torch.frombuffer(bytearray(it[src_key]), dtype=torch.uint8)
             hdescs[i].pixels = h_out[i].data_ptr()
             hdescs[i].pixels_cap = storage_bytes
-            hdescs[i].width, hdescs[i].height = w, h
-            hdescs[i].volume, hdescs[i].depth = 8 * bpp, depth
+            if args.e2e_api == "files":
+                hdescs[i].file, hdescs[i].file_len = h_in.data_ptr() + at, n
+            else:
+                hdescs[i].idat = h_in.data_ptr() + at
+                hdescs[i].idat_len = n
+                hdescs[i].width, hdescs[i].height = w, h
+                hdescs[i].volume, hdescs[i].depth = 8 * bpp, depth
             at += n
         del d_pixels, d_idat, descs
         torch.cuda.empty_cache()
         ctx.trim()  # the device-resident leg's arenas would otherwise sit beside the lanes'
 
         def step_host():
-            ctx.check(L.pngb200_decode_batch(ctx.handle, hdescs, B, pkg.MEM_HOST))
+            if args.e2e_api == "files":
+                ctx.check(L.pngb200_png_decode_batch(ctx.handle, hdescs, B, pkg.MEM_HOST))
+                assert all(hdescs[i].status == 0 for i in range(0, B, max(1, B // 8)))
+            else:
+                ctx.check(L.pngb200_decode_batch(ctx.handle, hdescs, B, pkg.MEM_HOST))
 
         for _ in range(2):
             step_host()
@@ -334,9 +356,12 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * npix * esteps / float(dt.item()) / 1e6, "unit": "MPixels/s",
                "h2d_bytes_per_step": comp_total, "d2h_bytes_per_step": B * storage_bytes, "steps": esteps,
-               "images_per_gpu": B,
-               "note": "pngb200_decode_batch with pinned HOST buffers: H2D of the IDAT streams and D2H of the "
-                       "decoded pixels are inside the timed region (host wall clock, max over ranks)"}
+               "images_per_gpu": B, "api": "pngb200_png_decode_batch" if args.e2e_api == "files" else "pngb200_decode_batch",
+               "note": ("whole PNG files (65544-byte IDAT chunks) in pinned HOST memory: chunk walk on the host, "
+                        "chunk CRC-32, IDAT gather, inflate and unfilter on the device; "
+                        if args.e2e_api == "files" else "pngb200_decode_batch with pinned HOST buffers: ") +
+                       "H2D of the compressed bytes and D2H of the decoded pixels are inside the timed region "
+                       "(host wall clock, max over ranks)"}
         if args.e2e_sweep:
             sweep = {}
             for cfg in args.e2e_sweep.split(","):

@@ -118,7 +118,10 @@ struct WaveParams {
 };
 
 constexpr int WAVE_WARPS   = 8;
-constexpr int WAVE_PUBLISH = 4;  // publish progress every this many chunks
+#ifndef PNGB200_WAVE_PUBLISH
+#define PNGB200_WAVE_PUBLISH 8
+#endif
+constexpr int WAVE_PUBLISH = PNGB200_WAVE_PUBLISH;  // publish progress every this many chunks
 
 template <int BPP>
 __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_prev, uint32_t* prog_mine)
@@ -146,7 +149,14 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
     uint32_t a0 = 0, a1 = 0, c0 = 0, c1 = 0;  // BPP 4/8 histories (words)
     uint64_t ah = 0, ch = 0;                  // generic byte histories
     uint32_t seen = 0;
+    uint4    upn = make_uint4(0, 0, 0, 0);  // lane 0: the chunk of the row above for the next step
+    bool     upn_ok = false;
+    // input chunks are fetched two steps ahead of their use (qcur = chunk j, qnext = j + 1, qfar = j + 2)
+    // and the line after next is pulled into L2: with ~40 warps x 32 rows per SM the rows' lines do not
+    // survive in L1 (3 % hit rate under ncu), so every load is an L2 round trip that has to be hidden
+    uint4 qnext = make_uint4(0, 0, 0, 0);
     if (active && nq > 0) qcur = inq[0];
+    if (active && nq > 1) qnext = inq[1];
 
     for (int S = 0; S < nchunk + 32; ++S) {
         const int j = S - (int)lane;
@@ -156,20 +166,36 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
         up.z = __shfl_up_sync(0xffffffffu, mine.z, 1);
         up.w = __shfl_up_sync(0xffffffffu, mine.w, 1);
         if (lane == 0) {
+            // the band above publishes its last row chunk by chunk; its chunk j + 1 is fetched while chunk j
+            // is being used, so the L2 round trip of that load is off the warp's critical path
             up = make_uint4(0, 0, 0, 0);
             if (active && above != nullptr && j < nchunk) {
-                while (seen <= (uint32_t)j) {
-                    seen = ld_volatile_u32(prog_prev);
-                    if (seen <= (uint32_t)j) __nanosleep(64);
+                if (upn_ok) {
+                    up = upn;
+                } else {
+                    while (seen <= (uint32_t)j) {
+                        seen = ld_volatile_u32(prog_prev);
+                        if (seen <= (uint32_t)j) __nanosleep(64);
+                    }
+                    up = load16_any(above + 16 * (uint64_t)j, true);
                 }
-                up = load16_any(above + 16 * (uint64_t)j, true);
+                upn_ok = false;
+                if (j + 1 < nchunk) {
+                    if (seen <= (uint32_t)(j + 1)) seen = ld_volatile_u32(prog_prev);
+                    if (seen > (uint32_t)(j + 1)) {
+                        upn = load16_any(above + 16 * (uint64_t)(j + 1), true);
+                        upn_ok = true;
+                    }
+                }
             }
         }
         if (active && j >= 0 && j < nchunk) {
-            uint4 qnext = make_uint4(0, 0, 0, 0);
-            if (j + 1 < nq) qnext = inq[j + 1];
+            uint4 qfar = make_uint4(0, 0, 0, 0);
+            if (j + 2 < nq) qfar = inq[j + 2];
+            if ((j & 7) == 0 && j + 24 < nq) asm volatile("prefetch.global.L2 [%0];" ::"l"(inq + j + 24));
             uint4 x = m == 0 ? qcur : shift_bytes(qcur, qnext, m);
             qcur = qnext;
+            qnext = qfar;
             uint4 o;
             if (BPP == 4) {
                 o.x = __vadd4(x.x, predict4(type, a1, up.x, c1, any_paeth));
