@@ -549,14 +549,25 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     //      depends on smaller offsets, so a lane may simply block on its current item
                     //      (items t, t + 512, ... in order): the smallest open item is always ready ----
                     if (!sh.anomaly && np) {
+                        // the list lives in L2: the item after the current one is fetched while the current
+                        // one is being copied
                         uint32_t idx  = t;
-                        CopyItem it   = CopyItem{0, 0};
-                        bool     have = false;
+                        CopyItem it   = CopyItem{0, 0}, nxt = CopyItem{0, 0};
+                        bool     have = false, have_nxt = false;
+                        if (idx < np) {
+                            nxt = list[idx];
+                            idx += PAR_THREADS;
+                            have_nxt = true;
+                        }
                         for (;;) {
-                            if (!have && idx < np) {
-                                it   = list[idx];
-                                idx += PAR_THREADS;
+                            if (!have && have_nxt) {
+                                it = nxt;
                                 have = true;
+                                have_nxt = idx < np;
+                                if (have_nxt) {
+                                    nxt = list[idx];
+                                    idx += PAR_THREADS;
+                                }
                             }
                             bool progressed = false;
                             if (have) {
@@ -574,7 +585,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                                 }
                             }
                             ++resolve_rounds;
-                            if (!__any_sync(0xffffffffu, have || idx < np)) break;
+                            if (!__any_sync(0xffffffffu, have || have_nxt)) break;
                             if (!__any_sync(0xffffffffu, progressed)) __nanosleep(40);
                         }
                     }

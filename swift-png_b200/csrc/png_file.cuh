@@ -220,10 +220,19 @@ int ensure_crc_tables(pngb200_ctx* ctx)
     return PNGB200_OK;
 }
 
-// CRC-32 of `regions` (device pointers) -> host vector
-int run_crc(pngb200_ctx* ctx, const std::vector<CrcRegion>& regions, uint32_t* d_acc_out, std::vector<uint32_t>* host_out)
+// CRC-32 of `regions` (device pointers) in three enqueue steps, so that a caller can put the small
+// table upload in front of its bulk H2D copies and the small result download behind its kernels (copies
+// of one direction are served in issue order across all streams: a few KB queued behind another lane's
+// gigabyte would stall this lane for its whole duration).
+struct CrcPlan {
+    CrcParams p;
+    size_t    acc_bytes = 0, off_acc = 0;
+    bool      any = false;
+};
+int crc_upload(pngb200_ctx* ctx, const std::vector<CrcRegion>& regions, uint32_t* d_acc_out, CrcPlan* plan)
 {
     const size_t count = regions.size();
+    plan->any = count != 0;
     if (count == 0) return PNGB200_OK;
     int rc = ensure_crc_tables(ctx);
     if (rc != PNGB200_OK) return rc;
@@ -244,28 +253,55 @@ int run_crc(pngb200_ctx* ctx, const std::vector<CrcRegion>& regions, uint32_t* d
     CU(cudaMemcpyAsync(ctx->d_crc.p, ctx->h_crc.p, off_base + bb, cudaMemcpyHostToDevice, ctx->stream));
     uint32_t* acc = d_acc_out ? d_acc_out : (uint32_t*)((char*)ctx->d_crc.p + off_acc);
     CU(cudaMemsetAsync(acc, 0, ab, ctx->stream));
-    CrcParams p;
-    p.regions = ctx->d_crc.as<CrcRegion>();
-    p.piece_base = (const uint32_t*)((char*)ctx->d_crc.p + off_base);
-    p.acc = acc;
-    p.tables = ctx->d_crctab.as<uint32_t>();
-    p.count = (uint32_t)count;
-    p.total_pieces = (uint32_t)pieces;
-    crc_regions_kernel<<<(unsigned)pieces, CRC_THREADS, 0, ctx->stream>>>(p);
+    plan->p.regions = ctx->d_crc.as<CrcRegion>();
+    plan->p.piece_base = (const uint32_t*)((char*)ctx->d_crc.p + off_base);
+    plan->p.acc = acc;
+    plan->p.tables = ctx->d_crctab.as<uint32_t>();
+    plan->p.count = (uint32_t)count;
+    plan->p.total_pieces = (uint32_t)pieces;
+    plan->acc_bytes = ab, plan->off_acc = off_acc;
+    return PNGB200_OK;
+}
+int crc_launch(pngb200_ctx* ctx, const CrcPlan& plan)
+{
+    if (!plan.any) return PNGB200_OK;
+    crc_regions_kernel<<<plan.p.total_pieces, CRC_THREADS, 0, ctx->stream>>>(plan.p);
     ctx->launches++;
     CU(cudaGetLastError());
-    if (host_out) {
-        host_out->resize(count);
-        CU(cudaMemcpyAsync((char*)ctx->h_crc.p + off_acc, acc, ab, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        memcpy(host_out->data(), (char*)ctx->h_crc.p + off_acc, ab);
-    }
+    return PNGB200_OK;
+}
+// enqueue the download of the results into pinned memory; valid after the stream's next synchronisation
+int crc_fetch(pngb200_ctx* ctx, const CrcPlan& plan, const uint32_t** pinned_out)
+{
+    *pinned_out = nullptr;
+    if (!plan.any) return PNGB200_OK;
+    CU(cudaMemcpyAsync((char*)ctx->h_crc.p + plan.off_acc, plan.p.acc, plan.acc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    *pinned_out = (const uint32_t*)((char*)ctx->h_crc.p + plan.off_acc);
+    return PNGB200_OK;
+}
+// all three at once; host_out: wait for the results
+int run_crc(pngb200_ctx* ctx, const std::vector<CrcRegion>& regions, uint32_t* d_acc_out, std::vector<uint32_t>* host_out)
+{
+    CrcPlan plan;
+    int rc = crc_upload(ctx, regions, d_acc_out, &plan);
+    if (rc == PNGB200_OK) rc = crc_launch(ctx, plan);
+    if (rc != PNGB200_OK || !host_out || !plan.any) return rc;
+    const uint32_t* pinned = nullptr;
+    rc = crc_fetch(ctx, plan, &pinned);
+    if (rc != PNGB200_OK) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    host_out->assign(pinned, pinned + regions.size());
     return PNGB200_OK;
 }
 
-int run_segment_copy(pngb200_ctx* ctx, const std::vector<CopySegment>& segs)
+struct CopyPlan {
+    CopyParams p;
+    bool       any = false;
+};
+int copy_upload(pngb200_ctx* ctx, const std::vector<CopySegment>& segs, CopyPlan* plan)
 {
     const size_t count = segs.size();
+    plan->any = count != 0;
     if (count == 0) return PNGB200_OK;
     std::vector<uint32_t> base(count + 1);
     uint64_t pieces = 0;
@@ -281,19 +317,33 @@ int run_segment_copy(pngb200_ctx* ctx, const std::vector<CopySegment>& segs)
     memcpy(ctx->h_seg.p, segs.data(), sb);
     memcpy((char*)ctx->h_seg.p + off_base, base.data(), bb);
     CU(cudaMemcpyAsync(ctx->d_seg.p, ctx->h_seg.p, off_base + bb, cudaMemcpyHostToDevice, ctx->stream));
-    CopyParams p;
-    p.segments = ctx->d_seg.as<CopySegment>();
-    p.piece_base = (const uint32_t*)((char*)ctx->d_seg.p + off_base);
-    p.count = (uint32_t)count;
-    p.total_pieces = (uint32_t)pieces;
-    segment_copy_kernel<<<(unsigned)pieces, CRC_THREADS, 0, ctx->stream>>>(p);
+    plan->p.segments = ctx->d_seg.as<CopySegment>();
+    plan->p.piece_base = (const uint32_t*)((char*)ctx->d_seg.p + off_base);
+    plan->p.count = (uint32_t)count;
+    plan->p.total_pieces = (uint32_t)pieces;
+    return PNGB200_OK;
+}
+int copy_launch(pngb200_ctx* ctx, const CopyPlan& plan)
+{
+    if (!plan.any) return PNGB200_OK;
+    segment_copy_kernel<<<plan.p.total_pieces, CRC_THREADS, 0, ctx->stream>>>(plan.p);
     ctx->launches++;
     CU(cudaGetLastError());
     return PNGB200_OK;
 }
+int run_segment_copy(pngb200_ctx* ctx, const std::vector<CopySegment>& segs)
+{
+    CopyPlan plan;
+    int rc = copy_upload(ctx, segs, &plan);
+    return rc != PNGB200_OK ? rc : copy_launch(ctx, plan);
+}
 
-// one chunk of a png_decode batch on one context
-int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int memspace)
+// One chunk of a png_decode batch on one context.  `optimistic`: the chunk CRCs are computed on the
+// device while the decode is already running on the assumption that they all match (no host round trip
+// between the two); the rare file whose CRC failure changes what the decoder may see -- a bad chunk
+// before the end of its IDAT run -- is put through the exact order once more (`optimistic` = false:
+// CRCs first, then the decode of just the IDAT chunks lexed before the failure).
+int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int memspace, bool optimistic = true)
 {
     DeviceGuard guard(ctx->device);
     const bool host_pixels = memspace == PNGB200_MEM_HOST;
@@ -318,18 +368,26 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
     std::vector<size_t>    region_base(count + 1);
     for (size_t i = 0; i < count; ++i) {
         region_base[i] = regions.size();
-        const FileWalk& w = walks[i];
-        if (w.chunks.empty()) continue;
-        const ChunkRec& last = w.chunks.back();
-        CU(cudaMemcpyAsync(ctx->d_file.as<uint8_t>() + f_off[i], d[i].file, last.off + 12 + (size_t)last.len,
-                           cudaMemcpyHostToDevice, ctx->stream));
-        for (const ChunkRec& c : w.chunks)
+        for (const ChunkRec& c : walks[i].chunks)
             regions.push_back({ctx->d_file.as<uint8_t>() + f_off[i] + c.off + 4, (uint64_t)c.len + 4, 0, 0});
     }
     region_base[count] = regions.size();
+    auto upload_files = [&]() -> int {
+        for (size_t i = 0; i < count; ++i) {
+            if (walks[i].chunks.empty()) continue;
+            const ChunkRec& last = walks[i].chunks.back();
+            CU(cudaMemcpyAsync(ctx->d_file.as<uint8_t>() + f_off[i], d[i].file, last.off + 12 + (size_t)last.len,
+                               cudaMemcpyHostToDevice, ctx->stream));
+        }
+        return PNGB200_OK;
+    };
     std::vector<uint32_t> crc;
-    int rc = run_crc(ctx, regions, nullptr, &crc);
-    if (rc != PNGB200_OK) return rc;
+    const uint32_t*       crc_late = nullptr;
+    int rc = PNGB200_OK;
+    if (!optimistic) {
+        if ((rc = upload_files()) != PNGB200_OK) return rc;
+        if ((rc = run_crc(ctx, regions, nullptr, &crc)) != PNGB200_OK) return rc;
+    }
     // Resolve where the reference's loop would have stopped lexing: the first chunk, in file order, with
     // a bad CRC or a structural error (a lexing error precedes that chunk's CRC check, a parsing /
     // ordering error follows it).
@@ -345,7 +403,7 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
         Plan& p = plans[i];
         p.stop = w.stop, p.status = w.status, p.a = w.a, p.b = w.b;
         for (size_t k = 0; k < w.chunks.size(); ++k) {
-            if (k > w.stop || (k == w.stop && w.stop_before_crc)) break;
+            if (optimistic || k > w.stop || (k == w.stop && w.stop_before_crc)) break;
             if (crc[region_base[i] + k] != w.chunks[k].declared) {
                 p.stop = k, p.status = PNGB200_ERR_LEX_INVALID_CHUNK_CHECKSUM, p.a = w.chunks[k].declared, p.b = crc[region_base[i] + k];
                 break;
@@ -402,18 +460,51 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
         }
         if (host_pixels) images[j].pixels = ctx->d_out.as<uint8_t>() + o_off[i];
     }
-    rc = run_segment_copy(ctx, segs);
-    if (rc != PNGB200_OK) return rc;
+    CrcPlan crc_plan;
+    if (optimistic) {
+        // issue order: small tables, bulk files, kernels, decode, and only then the small CRC download
+        CopyPlan copy_plan;
+        if ((rc = crc_upload(ctx, regions, nullptr, &crc_plan)) != PNGB200_OK) return rc;
+        if ((rc = copy_upload(ctx, segs, &copy_plan)) != PNGB200_OK) return rc;
+        if ((rc = upload_files()) != PNGB200_OK) return rc;
+        if ((rc = crc_launch(ctx, crc_plan)) != PNGB200_OK) return rc;
+        if ((rc = copy_launch(ctx, copy_plan)) != PNGB200_OK) return rc;
+    } else {
+        if ((rc = run_segment_copy(ctx, segs)) != PNGB200_OK) return rc;
+    }
     if (!images.empty()) {
         rc = pngb200_decode_batch_enqueue(ctx, images.data(), images.size(), PNGB200_MEM_DEVICE);
         if (rc != PNGB200_OK) return rc;
+    }
+    if (optimistic && (rc = crc_fetch(ctx, crc_plan, &crc_late)) != PNGB200_OK) return rc;
+    if (!images.empty()) {
         rc = pngb200_decode_batch_finish(ctx, images.data(), images.size());
         if (rc != PNGB200_OK) return rc;
     }
-    std::vector<int> decoded(count, 1);  // 1 = no decode ran
+    std::vector<size_t> redo;
+    std::vector<char>   skip(count, 0);
+    if (optimistic) {
+        CU(cudaStreamSynchronize(ctx->stream));  // the CRCs have landed in pinned memory
+        for (size_t i = 0; i < count; ++i) {
+            const FileWalk& w = walks[i];
+            for (size_t k = 0; k < w.chunks.size(); ++k) {
+                if (k > w.stop || (k == w.stop && w.stop_before_crc)) break;
+                const uint32_t computed = crc_late[region_base[i] + k];
+                if (computed == w.chunks[k].declared) continue;
+                if (k < plans[i].idat_hi && k > plans[i].idat_lo) {
+                    redo.push_back(i), skip[i] = 1;  // the decoder was shown IDAT chunks it should not have seen
+                } else {
+                    plans[i].stop = k, plans[i].status = PNGB200_ERR_LEX_INVALID_CHUNK_CHECKSUM;
+                    plans[i].a = w.chunks[k].declared, plans[i].b = computed;
+                    if (k <= plans[i].idat_lo && plans[i].idat_hi > plans[i].idat_lo) skip[i] = 2;  // failed before any IDAT
+                }
+                break;
+            }
+        }
+    }
     for (size_t j = 0; j < images.size(); ++j) {
         const size_t i = owner[j];
-        decoded[i] = images[j].status;
+        if (skip[i]) continue;
         d[i].checksum = images[j].checksum, d[i].blocks = images[j].blocks, d[i].produced = images[j].produced;
         const bool hard = images[j].status < 0 && images[j].status != PNGB200_ERR_PNG_INCOMPLETE_DATASTREAM;
         if (hard) {
@@ -426,7 +517,20 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
             CU(cudaMemcpyAsync(d[i].pixels, images[j].pixels, d[i].storage_size, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    for (size_t i = 0; i < count; ++i) d[i].status = plans[i].status, d[i].err_a = plans[i].a, d[i].err_b = plans[i].b;
+    for (size_t i = 0; i < count; ++i) {
+        d[i].status = plans[i].status, d[i].err_a = plans[i].a, d[i].err_b = plans[i].b;
+        if (skip[i] == 2) d[i].checksum = d[i].blocks = 0, d[i].produced = 0;
+    }
+    if (!redo.empty()) {
+        std::vector<pngb200_png_desc> again(redo.size());
+        for (size_t r = 0; r < redo.size(); ++r) again[r] = d[redo[r]];
+        rc = png_decode_some(ctx, again.data(), again.size(), memspace, false);
+        if (rc != PNGB200_OK) return rc;
+        for (size_t r = 0; r < redo.size(); ++r) {
+            d[redo[r]] = again[r];
+            d[redo[r]].format.palette = d[redo[r]].palette_rgba;
+        }
+    }
     return PNGB200_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -110,6 +111,10 @@ struct pngb200_ctx {
     // helper contexts (own stream + workspaces) that pipeline big host-memory batches: while one
     // lane's PCIe copies run, another lane's kernels do
     std::vector<pngb200_ctx*> lanes;
+    // Bulk H2D copies of the call in flight, issued by run_inflate after its own small table uploads and
+    // right before its first launch: copies of one direction are served in issue order across all
+    // streams, so a table queued behind another lane's gigabyte would hold this lane's kernels back.
+    std::function<int()> bulk_h2d;
 };
 
 namespace {
@@ -155,7 +160,15 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
     StreamJob*    d_jobs    = ctx->d_jobs.as<StreamJob>();
     StreamResult* d_results = ctx->d_results.as<StreamResult>();
     CU(cudaMemsetAsync(d_results, 0, sizeof(StreamResult) * count, ctx->stream));
-    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    auto before_first_launch = [&]() -> int {
+        int rc = PNGB200_OK;
+        if (ctx->bulk_h2d) {
+            rc = ctx->bulk_h2d();
+            ctx->bulk_h2d = nullptr;
+        }
+        if (rc == PNGB200_OK) CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        return rc;
+    };
     // big streams get a whole CTA each (block-parallel kernel); tiny ones a warp each
     {
         std::vector<uint32_t> par, ser;
@@ -175,6 +188,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
         std::copy(ser.begin(), ser.end(), ho + par.size());
         CU(cudaMemcpyAsync(ctx->d_order.p, ho, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
         const uint32_t* d_order = ctx->d_order.as<uint32_t>();
+        bool hooked = false;
         if (!par.empty()) {
             uint64_t max_cap = 0;
             for (uint32_t i : par) max_cap = std::max<uint64_t>(max_cap, h_jobs[i].dst_cap);
@@ -198,9 +212,13 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             pp.order = d_order;
             pp.scratch = ctx->d_scratch.as<uint8_t>();
             pp.count = (int)par.size();
+            if (int rc = before_first_launch()) return rc;
+            hooked = true;
             inflate_parallel_kernel<<<grid, PAR_THREADS, sizeof(ParShared), ctx->stream>>>(pp);
             ctx->launches++;
         }
+        if (!hooked)
+            if (int rc = before_first_launch()) return rc;
         if (!ser.empty()) {
             inflate_serial_kernel<<<(unsigned)ser.size(), 32, 0, ctx->stream>>>(d_jobs, d_results, d_order + par.size(),
                                                                                  (int)ser.size());
@@ -649,10 +667,13 @@ int pngb200_decode_batch_enqueue(pngb200_ctx* ctx, pngb200_image_desc* im, size_
     if (host) {
         CU(ctx->d_in.reserve(in_total));
         CU(ctx->d_out.reserve(out_total));
-        for (size_t i = 0; i < count; ++i)
-            if (im[i].idat_len)
-                CU(cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + in_off[i], im[i].idat, im[i].idat_len,
-                                   cudaMemcpyHostToDevice, ctx->stream));
+        ctx->bulk_h2d = [ctx, im, count, &in_off]() -> int {  // runs inside run_inflate below, after its tables
+            for (size_t i = 0; i < count; ++i)
+                if (im[i].idat_len)
+                    CU(cudaMemcpyAsync(ctx->d_in.as<uint8_t>() + in_off[i], im[i].idat, im[i].idat_len,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+            return PNGB200_OK;
+        };
     }
     StreamJob* jobs = ctx->h_jobs.as<StreamJob>();
     for (size_t i = 0; i < count; ++i) {
@@ -667,6 +688,7 @@ int pngb200_decode_batch_enqueue(pngb200_ctx* ctx, pngb200_image_desc* im, size_
     }
     CU(cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(StreamJob) * count, cudaMemcpyHostToDevice, ctx->stream));
     int rc = run_inflate(ctx, jobs, count);
+    ctx->bulk_h2d = nullptr;  // captured this frame's locals
     if (rc != PNGB200_OK) return rc;
     std::vector<UnfilterItem> items(count);
     for (size_t i = 0; i < count; ++i) {
