@@ -348,36 +348,81 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
     DeviceGuard guard(ctx->device);
     const bool host_pixels = memspace == PNGB200_MEM_HOST;
     std::vector<FileWalk> walks(count);
-    std::vector<size_t>   f_off(count);
-    size_t f_total = 0;
+    // Device image of a file: [bytes in front of the first IDAT | bytes behind the IDAT run] in the file
+    // arena, and the bodies of the IDAT run back to back in the payload arena.  The H2D copy itself
+    // does the concatenation: a run of equal-sized IDAT chunks (what every encoder writes, the reference
+    // included) is one pitched copy (cudaMemcpy2DAsync: row = body, source pitch = body + 12).
+    std::vector<size_t> f_off(count), g_off(count), pre_len(count), post_at(count), post_len(count);
+    size_t f_total = 0, g_total = 0;
     for (size_t i = 0; i < count; ++i) {
         if (!d[i].file && d[i].file_len) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "file %zu: null pointer", i);
-        walk_file(d[i], walks[i]);
-        d[i].chunks = (uint32_t)walks[i].chunks.size();
+        FileWalk& w = walks[i];
+        walk_file(d[i], w);
+        d[i].chunks = (uint32_t)w.chunks.size();
         d[i].status = PNGB200_OK, d[i].err_a = d[i].err_b = 0;
         d[i].checksum = d[i].blocks = 0, d[i].produced = 0;
-        f_off[i] = f_total;
-        f_total += align_up(d[i].file_len + 16, 256);
-        if (walks[i].first_idat != (size_t)-1 && (!d[i].pixels || d[i].pixels_cap < d[i].storage_size))
+        if (w.first_idat != (size_t)-1 && (!d[i].pixels || d[i].pixels_cap < d[i].storage_size))
             return set_error(ctx, PNGB200_ERR_OUTPUT_CAPACITY, "file %zu: pixels_cap %zu < %llu", i, d[i].pixels_cap,
                              (unsigned long long)d[i].storage_size);
+        const size_t lexed = w.chunks.empty() ? 0 : (size_t)(w.chunks.back().off + 12 + w.chunks.back().len);
+        if (w.first_idat == (size_t)-1) {
+            pre_len[i] = lexed, post_at[i] = lexed, post_len[i] = 0;
+        } else {
+            pre_len[i] = (size_t)w.chunks[w.first_idat].off;
+            post_at[i] = w.idat_end < w.chunks.size() ? (size_t)w.chunks[w.idat_end].off : lexed;
+            post_len[i] = lexed - post_at[i];
+        }
+        f_off[i] = f_total;
+        f_total += align_up(pre_len[i] + post_len[i] + 16, 256);
+        g_off[i] = g_total;
+        g_total += align_up(d[i].idat_bytes + 16, 256);
     }
-    // the files go to HBM once; chunks that were lexed get their CRC checked there
-    CU(ctx->d_file.reserve(f_total));
+    CU(ctx->d_file.reserve(std::max<size_t>(f_total, 256)));
+    CU(ctx->d_in.reserve(std::max<size_t>(g_total, 256)));
+    // every lexed chunk's CRC region (type + body): in the file arena, or -- IDAT run -- the body in the
+    // payload arena with the type folded in as a prefix
     std::vector<CrcRegion> regions;
     std::vector<size_t>    region_base(count + 1);
     for (size_t i = 0; i < count; ++i) {
         region_base[i] = regions.size();
-        for (const ChunkRec& c : walks[i].chunks)
-            regions.push_back({ctx->d_file.as<uint8_t>() + f_off[i] + c.off + 4, (uint64_t)c.len + 4, 0, 0});
+        const FileWalk& w = walks[i];
+        uint8_t* const  meta = ctx->d_file.as<uint8_t>() + f_off[i];
+        uint8_t*        body = ctx->d_in.as<uint8_t>() + g_off[i];
+        for (size_t k = 0; k < w.chunks.size(); ++k) {
+            const ChunkRec& c = w.chunks[k];
+            if (w.first_idat != (size_t)-1 && k >= w.first_idat && k < w.idat_end) {
+                regions.push_back({body, (uint64_t)c.len, CK_IDAT, 1});
+                body += c.len;
+            } else {
+                const size_t at = c.off < pre_len[i] ? (size_t)c.off : pre_len[i] + ((size_t)c.off - post_at[i]);
+                regions.push_back({meta + at + 4, (uint64_t)c.len + 4, 0, 0});
+            }
+        }
     }
     region_base[count] = regions.size();
     auto upload_files = [&]() -> int {
         for (size_t i = 0; i < count; ++i) {
-            if (walks[i].chunks.empty()) continue;
-            const ChunkRec& last = walks[i].chunks.back();
-            CU(cudaMemcpyAsync(ctx->d_file.as<uint8_t>() + f_off[i], d[i].file, last.off + 12 + (size_t)last.len,
-                               cudaMemcpyHostToDevice, ctx->stream));
+            const FileWalk& w = walks[i];
+            uint8_t* const  meta = ctx->d_file.as<uint8_t>() + f_off[i];
+            if (pre_len[i]) CU(cudaMemcpyAsync(meta, d[i].file, pre_len[i], cudaMemcpyHostToDevice, ctx->stream));
+            if (post_len[i])
+                CU(cudaMemcpyAsync(meta + pre_len[i], d[i].file + post_at[i], post_len[i], cudaMemcpyHostToDevice, ctx->stream));
+            if (w.first_idat == (size_t)-1) continue;
+            uint8_t* body = ctx->d_in.as<uint8_t>() + g_off[i];
+            for (size_t k = w.first_idat; k < w.idat_end;) {
+                const uint32_t len = w.chunks[k].len;
+                size_t run = 1;
+                while (k + run < w.idat_end && w.chunks[k + run].len == len) ++run;
+                const uint8_t* src = d[i].file + w.chunks[k].off + 8;
+                if (len == 0) {
+                } else if (run == 1) {
+                    CU(cudaMemcpyAsync(body, src, len, cudaMemcpyHostToDevice, ctx->stream));
+                } else {
+                    CU(cudaMemcpy2DAsync(body, len, src, (size_t)len + 12, len, run, cudaMemcpyHostToDevice, ctx->stream));
+                }
+                body += (size_t)len * run;
+                k += run;
+            }
         }
         return PNGB200_OK;
     };
@@ -395,9 +440,8 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
     std::vector<Plan> plans(count);
     std::vector<pngb200_image_desc> images;
     std::vector<size_t>             owner;
-    std::vector<CopySegment>        segs;
-    std::vector<size_t>             g_off(count), o_off(count);
-    size_t g_total = 0, o_total = 0;
+    std::vector<size_t>             o_off(count);
+    size_t o_total = 0;
     for (size_t i = 0; i < count; ++i) {
         const FileWalk& w = walks[i];
         Plan& p = plans[i];
@@ -420,14 +464,7 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
         for (size_t k = p.idat_lo; k < p.idat_hi; ++k) payload += w.chunks[k].len;
         pngb200_image_desc im;
         memset(&im, 0, sizeof im);
-        uint8_t* file_dev = ctx->d_file.as<uint8_t>() + f_off[i];
-        if (p.idat_hi - p.idat_lo == 1) {
-            im.idat = file_dev + w.chunks[p.idat_lo].off + 8;  // a single IDAT is decoded where it lies
-        } else {
-            g_off[i] = g_total;
-            g_total += align_up(payload + 16, 256);
-            im.idat = (const uint8_t*)(uintptr_t)1;  // patched below once the gather arena exists
-        }
+        im.idat = ctx->d_in.as<uint8_t>() + g_off[i];  // the chunks pushed so far are a prefix of the gathered run
         im.idat_len = payload;
         if (host_pixels) {
             o_off[i] = o_total;
@@ -443,34 +480,15 @@ int png_decode_some(pngb200_ctx* ctx, pngb200_png_desc* d, size_t count, int mem
         images.push_back(im);
         owner.push_back(i);
     }
-    if (g_total) CU(ctx->d_in.reserve(g_total));
     if (o_total) CU(ctx->d_out.reserve(o_total));
-    for (size_t j = 0; j < images.size(); ++j) {
-        const size_t i = owner[j];
-        const FileWalk& w = walks[i];
-        const Plan& p = plans[i];
-        if (p.idat_hi - p.idat_lo > 1) {
-            uint8_t* dst = ctx->d_in.as<uint8_t>() + g_off[i];
-            images[j].idat = dst;
-            for (size_t k = p.idat_lo; k < p.idat_hi; ++k) {
-                if (w.chunks[k].len)
-                    segs.push_back({ctx->d_file.as<uint8_t>() + f_off[i] + w.chunks[k].off + 8, dst, w.chunks[k].len});
-                dst += w.chunks[k].len;
-            }
-        }
-        if (host_pixels) images[j].pixels = ctx->d_out.as<uint8_t>() + o_off[i];
-    }
+    if (host_pixels)
+        for (size_t j = 0; j < images.size(); ++j) images[j].pixels = ctx->d_out.as<uint8_t>() + o_off[owner[j]];
     CrcPlan crc_plan;
     if (optimistic) {
-        // issue order: small tables, bulk files, kernels, decode, and only then the small CRC download
-        CopyPlan copy_plan;
+        // issue order: small table, bulk files, kernels, decode, and only then the small CRC download
         if ((rc = crc_upload(ctx, regions, nullptr, &crc_plan)) != PNGB200_OK) return rc;
-        if ((rc = copy_upload(ctx, segs, &copy_plan)) != PNGB200_OK) return rc;
         if ((rc = upload_files()) != PNGB200_OK) return rc;
         if ((rc = crc_launch(ctx, crc_plan)) != PNGB200_OK) return rc;
-        if ((rc = copy_launch(ctx, copy_plan)) != PNGB200_OK) return rc;
-    } else {
-        if ((rc = run_segment_copy(ctx, segs)) != PNGB200_OK) return rc;
     }
     if (!images.empty()) {
         rc = pngb200_decode_batch_enqueue(ctx, images.data(), images.size(), PNGB200_MEM_DEVICE);
