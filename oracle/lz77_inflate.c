@@ -362,10 +362,21 @@ static int read_be32_aligned(stream* s, uint32_t* v)
 
 static const int CODELENGTH_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+/* test hook: where each block header starts (bit offset, output offset, block type) */
+static __thread uint64_t* g_trace = NULL;
+static __thread size_t    g_trace_cap = 0, g_trace_n = 0;
+
 /* one DEFLATE block.  returns ORC_OK (block done), ORC_NEED_MORE_INPUT, or error; *final set */
 static int read_block(stream* s, itables* tb, int* final, orc_inflate_result* r)
 {
     const bitin* in = &s->in;
+    if (g_trace && s->b + 3 <= in_count(in)) {
+        if (g_trace_n < g_trace_cap) {
+            g_trace[3 * g_trace_n] = s->b, g_trace[3 * g_trace_n + 1] = s->out.end;
+            g_trace[3 * g_trace_n + 2] = in_bits(in, s->b + 1, 2);
+        }
+        g_trace_n++;
+    }
     /* ---- readBlockMetadata, Stream.swift:59-141 ---- */
     if (s->b + 3 > in_count(in)) return ORC_NEED_MORE_INPUT;
     *final = in_bits(in, s->b, 1) != 0;
@@ -540,4 +551,15 @@ void orc_inflate(int format, const uint8_t* in, size_t n, uint8_t* out, size_t c
     res->checksum = computed;
     if (s.out.owned) free(s.out.p);
     free(tb);
+}
+
+/* test hook for tools/block_probe.py: inflate while recording (bit offset, output offset, BTYPE) of
+ * every block header; returns the number of blocks (entries beyond cap are counted, not stored) */
+size_t orc_debug_block_starts(int format, const uint8_t* in, size_t n, uint64_t* trace, size_t cap)
+{
+    orc_inflate_result res;
+    g_trace = trace, g_trace_cap = cap, g_trace_n = 0;
+    orc_inflate(format, in, n, NULL, 0, &res);
+    g_trace = NULL;
+    return res.status == ORC_OK ? g_trace_n : 0;
 }

@@ -109,6 +109,7 @@ size_t orc_png_filtered_size(uint32_t w, uint32_t h, int volume, int interlaced)
 size_t orc_deflate(int format, int level, int exponent, const uint8_t* in, size_t n,
                    uint8_t* out, size_t cap);
 size_t orc_deflate_bound(size_t n);
+size_t orc_debug_block_starts(int format, const uint8_t* in, size_t n, uint64_t* trace, size_t cap);
 size_t orc_debug_greedy_parse(const uint8_t* in, size_t n, int exponent, long attempts, int goal,
                               int* runs, int* dists, size_t cap);
 
