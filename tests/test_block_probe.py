@@ -30,3 +30,20 @@ def test_probe_finds_exactly_the_true_boundaries(orc):
         found = L.probe_scan(z, len(z), 16, len(z) * 8, hist, hits, 4096)
         assert sorted(hits[i] for i in range(found)) == true_bits
         assert sum(hist) == len(z) * 8 - 16 and hist[1] > 0.7 * sum(hist)  # three quarters die on BTYPE alone
+
+
+def test_segment_model_is_bit_exact(orc):
+    """the whole planned pipeline on the CPU: search, independent segment decodes with a symbolic window,
+    chaining by exact arrival, marker resolution -- equals zlib's output whatever the split count"""
+    import segment_model
+    rng = np.random.default_rng(8)
+    streams = [corpus.zlib_png_stream(corpus.make("photo", 800, 600, 5), 4, 6)[1],
+               corpus.zlib_png_stream(corpus.make("graphic", 640, 480, 6), 4, 1)[1],
+               zlib.compress(bytes(rng.integers(0, 3, 600_000, dtype=np.uint8)), 2),
+               zlib.compress(bytes(rng.integers(0, 256, 100_000, dtype=np.uint8)), 6),
+               orc.deflate(corpus.zlib_png_stream(corpus.make("photo", 512, 384, 7), 4, 6)[0], 7)]
+    for z in streams:
+        for want in (1, 2, 7, 40):
+            got, rows, _ = segment_model.run(z, want)
+            assert got == zlib.decompress(z)
+            assert 1 <= len(rows) <= want and rows[0][2] == 0  # segment 0 knows its (empty) window: no markers
