@@ -191,7 +191,10 @@ def main():
             return
         items = make_corpus(args, None, None)
         threads = os.cpu_count() or 1
-        per_step = args.cpu_images or max(threads, 1)  # one image per host thread and step: every core busy
+        # one image per host thread and step (every core busy); 8K images are capped at 64 per step so that a
+        # step stays under ~10 s on the box (measured r01: 128 threads 269 MPixels/s, 16 threads 199)
+        per_step = args.cpu_images or max(min(threads, 64) if w * h > 4_000_000 else threads, 1)
+        threads = min(threads, per_step)
         for _ in range(max(args.warmup, 0) and 1):
             cpu_decode_rate(items, w, h, bpp, depth, min(per_step, threads), threads)
         t0 = time.perf_counter()
