@@ -55,7 +55,9 @@ def parse_args():
                          "our GPU encoder at --encode-level, bit-identical to the reference's own output "
                          "(slow for 8K: one warp per stream)")
     ap.add_argument("--inflate-mode", type=int, default=0)
-    ap.add_argument("--mode", default="decode", choices=["decode", "encode"])
+    ap.add_argument("--mode", default="decode", choices=["decode", "encode", "inflate"],
+                    help="inflate: BASELINE.json configs[4], standalone gzip streams of --sweep-mb sizes (device-resident)")
+    ap.add_argument("--sweep-mb", default="1,16,64", help="--mode inflate: uncompressed stream sizes in MiB")
     ap.add_argument("--encode-level", type=int, default=9)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: whole batch if <= 110 GB pinned)")
@@ -215,6 +217,8 @@ def main():
 
     if args.mode == "encode":
         return main_encode(args, w, h, bpp, depth, rank, local_rank, world, config)
+    if args.mode == "inflate":
+        return main_inflate(args, rank, local_rank, world)
 
     # ---------------- our arm ----------------
     import torch
@@ -433,6 +437,65 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def main_inflate(args, rank, local_rank, world):
+    """BASELINE.json configs[4]: standalone LZ77 / Gzip.Inflator throughput on gzip streams of S0 filtered
+    bytes, device-resident, one JSON line with a row per stream size.  One CTA
+    decodes one stream, so every size is run as min(592, ~6 GiB / size) independent streams."""
+    import zlib
+
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import corpus
+    torch.cuda.set_device(local_rank)
+    pkg = importlib.import_module("swift-png_b200")
+    ctx = pkg.Context(local_rank)
+    L = ctx._lib
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    base = b"".join(corpus.zlib_png_stream(corpus.make("photo", 2048, 1024, 0x5EED + k), 4, 6)[0] for k in range(2))
+    rows = []
+    for mb in [int(x) for x in args.sweep_mb.split(",")]:
+        n = mb << 20
+        plain = (base * (n // len(base) + 1))[:n]
+        co = zlib.compressobj(6, zlib.DEFLATED, 31)  # gzip wrapper
+        z = co.compress(plain) + co.flush()
+        count = max(1, min(592, (6 << 30) // n))
+        d_src = torch.frombuffer(bytearray(z), dtype=torch.uint8).cuda()
+        d_in = [d_src.clone() for _ in range(count)]
+        d_out = torch.empty((count, n), dtype=torch.uint8, device="cuda")
+        descs = (pkg.StreamDesc * count)()
+        for i in range(count):
+            descs[i].src, descs[i].src_len = d_in[i].data_ptr(), len(z)
+            descs[i].dst, descs[i].dst_cap = d_out[i].data_ptr(), n
+            descs[i].format = pkg.FORMAT_GZIP
+        for _ in range(2):
+            ctx.check(L.pngb200_inflate_batch(ctx.handle, descs, count, pkg.MEM_DEVICE))
+        assert all(descs[i].status == 0 and descs[i].produced == n for i in range(count))
+        assert descs[0].checksum == zlib.crc32(plain) and bytes(d_out[count - 1].cpu().numpy().tobytes()) == plain
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        steps = max(1, args.steps)
+        for _ in range(steps):
+            ctx.check(L.pngb200_inflate_batch(ctx.handle, descs, count, pkg.MEM_DEVICE))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        rows.append({"stream_mib": mb, "streams": count, "compressed_bytes": len(z), "ms_per_batch": ms,
+                     "out_GBps": count * n / ms / 1e6, "c_plus_u_GBps": count * (n + len(z)) / ms / 1e6,
+                     "per_stream_MBps": n / ms / 1e3})
+        del d_in, d_out, d_src
+        torch.cuda.empty_cache()
+        ctx.trim()
+    if rank == 0:
+        best = max(r["c_plus_u_GBps"] for r in rows)
+        print(json.dumps({"metric": "GB/s standalone gzip inflate (C+U)", "value": best, "unit": "GB/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": 2, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "gzip streams of S0 filtered bytes, zlib level 6 (BASELINE configs[4])"},
+                          "sweep": rows, "bit_exact": True}))
 
 
 def main_encode(args, w, h, bpp, depth, rank, local_rank, world, config):
