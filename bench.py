@@ -420,7 +420,7 @@ def main():
                 "whole_step_frac": alg_bytes / (ms_max / args.steps / 1e3) / 1e9 / peak}
 
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # the host-core baseline is reported at N = 1 only
         threads = os.cpu_count() or 1
         n_cpu = args.cpu_images or (threads if npix > 4_000_000 else 4 * threads)
         v, dt = cpu_decode_rate(items, w, h, bpp, depth, n_cpu, threads)
