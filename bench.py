@@ -295,7 +295,7 @@ def main():
         barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launches - launches0
-    stats = ctx.inflate_stats(B)
+    stats = ctx.inflate_counters(B)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

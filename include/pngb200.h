@@ -125,6 +125,15 @@ int          pngb200_ctx_stage_ms(pngb200_ctx* ctx, float ms[3]);
  * out[0] waves, out[1] sync rounds, out[2] copy-resolve rounds, out[3] streams that fell back to
  * the serial decoder (the analogue of the reference's -DDUMP_LZ77_BLOCKS statistics) */
 int          pngb200_ctx_inflate_stats(pngb200_ctx* ctx, size_t count, uint64_t out[4]);
+/* the full counter set of the last finished batch, summed over its `count` streams (the reference prints the
+ * same kind of numbers under -DDUMP_LZ77_BLOCKS / -DDUMP_LZ77_BLOCKS_STATISTICS,
+ * Sources/LZ77/Inflator/LZ77.InflatorBuffers.Stream.swift:11,292-297,364-374,472-486):
+ * out[0..3] as pngb200_ctx_inflate_stats (out[1] = tokens decoded by chain walks), out[4] tokens (literals +
+ * matches), out[5] matches, out[6] matches whose source was produced in the same 8 KiB wave by another
+ * thread (they wait in the deferred-copy list), out[7] DEFLATE blocks, out[8..19] SM cycles per phase of
+ * inflate_wave_kernel as seen by thread 0 of each CTA: header+tables, stage, speculate, walk, chain,
+ * count+scan, emit, resolve, store, stored blocks, (2 spare); out[20..23] reserved */
+int          pngb200_ctx_inflate_counters(pngb200_ctx* ctx, size_t count, uint64_t out[24]);
 
 /* ---- batched one-shot entry points (the throughput path) ---- */
 

@@ -223,6 +223,8 @@ def lib():
     L.pngb200_ctx_stage_ms.restype = C.c_int
     L.pngb200_ctx_inflate_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_inflate_stats.restype = C.c_int
+    L.pngb200_ctx_inflate_counters.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    L.pngb200_ctx_inflate_counters.restype = C.c_int
     L.pngb200_inflate_batch.argtypes = [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_int]
     L.pngb200_inflate_batch.restype = C.c_int
     for name in ("pngb200_decode_batch", "pngb200_decode_batch_enqueue", "pngb200_unfilter_batch"):
@@ -318,6 +320,16 @@ class Context:
         out = (C.c_uint64 * 4)()
         self.check(self._lib.pngb200_ctx_inflate_stats(self.handle, count, out))
         return dict(waves=out[0], sync_rounds=out[1], resolve_rounds=out[2], fallbacks=out[3])
+
+    def inflate_counters(self, count: int):
+        """all device-side counters of the last batch (see pngb200_ctx_inflate_counters)"""
+        out = (C.c_uint64 * 24)()
+        self.check(self._lib.pngb200_ctx_inflate_counters(self.handle, count, out))
+        names = ["header_tables", "stage", "speculate", "walk", "chain", "count_scan", "emit", "resolve", "store",
+                 "stored_blocks"]
+        return dict(waves=out[0], walk_tokens=out[1], resolve_rounds=out[2], fallbacks=out[3], tokens=out[4],
+                    matches=out[5], deferred_matches=out[6], blocks=out[7],
+                    cycles={n: out[8 + i] for i, n in enumerate(names)})
 
     def set_inflate_mode(self, mode: int):
         self._lib.pngb200_ctx_set_inflate_mode(self.handle, mode)

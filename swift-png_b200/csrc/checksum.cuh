@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(CK_THREADS) checksum_chunk_kernel(ChecksumPara
         if (p.chunk_base[mid] <= chunk) lo = mid;
         else hi = mid;
     }
+    if (p.results[lo].ck_done) return;  // zlib stream inflated by the wave kernel: Adler-32 came with the store
     const StreamJob job = p.jobs[lo];
     const uint64_t  n   = p.results[lo].produced;
     const uint64_t  off = (uint64_t)(chunk - p.chunk_base[lo]) * CK_CHUNK;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(32) checksum_fold_kernel(ChecksumParams p)
     if (j >= p.count) return;
     const unsigned  lane = lane_id();
     StreamResult*   r    = p.results + j;
+    if (r->ck_done) return;
     const StreamJob job  = p.jobs[j];
     const uint64_t  n    = r->produced;
     const uint32_t  c0   = p.chunk_base[j];

@@ -1,7 +1,13 @@
 // common.cuh -- device-side job/result records and small helpers shared by all kernels.
 #pragma once
 
+#ifdef PNGB200_EMU
+// host-side SIMT emulation of the kernels (tests/emu/simt.h): test infrastructure, never the product
+#include "simt.h"
+#else
 #include <cuda_runtime.h>
+#define PNGB200_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 #include <stdint.h>
 
 #include "../../include/pngb200.h"
@@ -34,6 +40,12 @@ struct StreamResult {
     uint32_t phase;           // phase to resume in at resume_bit (see StreamJob.phase)
     // device-side counters (the reference's -DDUMP_LZ77_BLOCKS style statistics)
     uint32_t stat_waves, stat_sync_rounds, stat_resolve_rounds, stat_fallback;
+    uint64_t stat_tokens, stat_matches, stat_deferred;  // tokens / LZ77 matches on the stream, matches that had to wait
+    uint32_t ck_done;         // 1: `checksum` was computed (and compared) by the inflate kernel itself
+    uint32_t pad_;
+    // SM cycles thread 0 of the stream's CTA spent per phase of the wave kernel (each ends at a barrier):
+    // 0 header+tables 1 stage 2 speculate 3 walk 4 chain 5 count+scan 6 emit 7 resolve 8 store 9 stored blocks
+    uint64_t stat_cycles[12];
 };
 
 // One image for the unfilter stage.
@@ -59,13 +71,21 @@ __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
 {
+#ifdef PNGB200_EMU
+    return *(const volatile uint32_t*)p;
+#else
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+#endif
 }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
 {
+#ifdef PNGB200_EMU
+    *(volatile uint32_t*)p = v;
+#else
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 
 }  // namespace pngb200

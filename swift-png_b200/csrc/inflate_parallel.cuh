@@ -101,6 +101,19 @@ struct ParParams {
 
 struct CopyItem { uint32_t o; uint32_t run_dist; };  // run | (dist - 1) << 16
 
+#ifdef PNGB200_EMU
+typedef uintptr_t saddr_t;
+inline uint32_t lds32(saddr_t addr) { return *(const uint32_t*)addr; }
+inline uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
+{
+    pos &= 0xff; len &= 0xff;   // PTX bfe.u32 semantics
+    if (len == 0 || pos > 31) return 0;
+    uint32_t v = x >> pos;
+    return len >= 32 ? v : v & ((1u << len) - 1u);
+}
+inline saddr_t smem_addr(const void* p) { return (uintptr_t)p; }
+#else
+typedef uint32_t saddr_t;
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
     uint32_t v;
@@ -114,14 +127,15 @@ __device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len
     return r;
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#endif
 
 struct FastBits {
-    uint32_t wbase;     // shared-memory address of the staged words
+    saddr_t  wbase;     // shared-memory address of the staged words
     uint32_t wi;        // next word to fetch
     uint32_t cur, nxt;
     uint32_t off;       // < 32 at every peek
     uint32_t pos;
-    __device__ __forceinline__ void init(uint32_t words_addr, uint32_t start)
+    __device__ __forceinline__ void init(saddr_t words_addr, uint32_t start)
     {
         wbase = words_addr;
         const uint32_t W = start >> 5;
@@ -147,7 +161,7 @@ struct FastBits {
 
 // one table lookup of the decode passes: root entry, subtable entry behind a pointer (rare)
 template <int ROOT>
-__device__ __forceinline__ uint32_t fast_lookup(uint32_t table_addr, uint32_t bits)
+__device__ __forceinline__ uint32_t fast_lookup(saddr_t table_addr, uint32_t bits)
 {
     uint32_t e = lds32(table_addr + ((bits & ((1u << ROOT) - 1u)) << 2));
     if ((e & (E_SPECIAL | E_PTR | E_INVALID)) == (E_SPECIAL | E_PTR))
@@ -206,7 +220,7 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
 {
     FastBits b;
     b.init(smem_addr(sh.words), start);
-    const uint32_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
+    const saddr_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
     nout  = 0;
     ncopy = 0;
     flags = 0;
@@ -313,7 +327,7 @@ __device__ __forceinline__ void lz_copy(uint8_t* img, const uint8_t* hbm, bool i
 
 __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel_kernel(ParParams P)
 {
-    extern __shared__ __align__(16) unsigned char par_smem[];
+    PNGB200_DYN_SMEM(par_smem);
     ParShared& sh = *reinterpret_cast<ParShared*>(par_smem);
     const uint32_t t    = threadIdx.x;
     const unsigned lane = lane_id(), warp = t >> 5;
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     if (t < nvalid) {
                         FastBits b;
                         b.init(smem_addr(sh.words), my_start);
-                        const uint32_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
+                        const saddr_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
                         uint32_t o = o_start;
                         uint32_t mw = o_start >> 5, mbits = 0;   // pending unresolved-bit word
                         while (b.pos < limit) {
@@ -649,12 +663,14 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
     }
 }
 
+#ifndef PNGB200_EMU
 // host side: opt in to the large dynamic shared memory on the current device (once per context)
 inline int configure_inflate_parallel()
 {
     return (int)cudaFuncSetAttribute(inflate_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(ParShared));
 }
+#endif
 
 inline uint64_t par_bitmap_words(uint64_t max_dst_cap)
 {

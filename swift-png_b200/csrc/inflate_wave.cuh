@@ -1,0 +1,1037 @@
+// inflate_wave.cuh -- intra-stream parallel DEFLATE inflate, second generation ("chain walk").
+//
+// One CTA of 256 threads eats a DEFLATE block in WAVES of 256 subsequences x 256 bits (8 KiB of
+// compressed data staged in shared memory, padded 9/8 so lane-strided word reads do not conflict).
+// DEFLATE has no sync markers, but Huffman codes self-synchronise: a decoder started at a wrong bit
+// falls into step with the true token sequence after a few tokens.  Round 1 exploited that with
+// CTA-wide re-decode rounds (3.2 decode passes per bit, ~12 barriers per wave).  Here every bit is
+// decoded about 1.2 times and a wave costs 8 barriers:
+//
+//   A. speculate  thread t decodes subsequence t from a guessed start (thread 0's is exact) until it
+//                 leaves the subsequence.  It records (i) a 256-bit map of the token start positions
+//                 it visited, (ii) the tokens themselves (<= WV_TCAP per thread, 32-bit: literal
+//                 byte, or run | distance), (iii) byte/copy totals, (iv) its exit position.
+//   B. walk       thread t continues from ITS exit position through the following subsequences until
+//                 it lands on a position the owner of that subsequence also visited (from there on
+//                 the two decodes are identical), or on end-of-block / the end of the wave.  Usually
+//                 a handful of tokens.
+//   C. resolve    the true token chain is the orbit of thread 0 under "t -> subsequence where t's
+//                 walk joined".  One thread follows it, jumping over the (rare) subsequences a walk
+//                 crossed without joining.  Every thread on the chain owns the chain segment from
+//                 the position where its predecessor joined it to the position where its own walk
+//                 joined the next one; the index of its first valid token is a popcount of its map.
+//   D. count      bytes / copies of the owned segment = totals - the garbage prefix (read back from
+//                 the staged tokens) + the walk's counts; CTA scan -> output offsets, list slots.
+//   E. emit       staged tokens are replayed (no Huffman decoding); only the short walk segment is
+//                 decoded again.  Literals go to a 16 KiB shared-memory image of the wave's output.
+//                 An LZ77 copy runs immediately when its source is final: behind the wave (already
+//                 in HBM -- in PNG the distance is about one scanline) or inside the thread's own
+//                 finished bytes (distance of a pixel or two).  Only copies that read another
+//                 thread's bytes of THIS wave are deferred to a list sorted by output offset, their
+//                 destination bytes flagged in an "unresolved" bitmap.
+//   F. resolve    barrier-free sweep of the deferred list (a copy runs once none of its source bytes
+//                 is flagged; the smallest open item is always ready).
+//   G. store      image -> HBM with 16-byte coalesced stores; the Adler-32 of the wave is taken from
+//                 the same registers (reassociated sums, folded per wave), so zlib streams need no
+//                 separate checksum pass over the inflated bytes.
+//
+// Waves that expand beyond the image (flat graphics: 8 KiB -> megabytes) write HBM directly and keep
+// their bitmap in HBM scratch.  Anything irregular (invalid symbol on the chain, truncation, output
+// overflow, distance before the start of the output) is not handled here: warp 0 re-runs the block
+// with the serial decoder (inflate_serial.cuh), which owns the exact error semantics of the
+// reference.
+//
+// CTAs are persistent: each takes streams from an atomic ticket (the host orders streams longest
+// first), so per-CTA scratch in HBM is bounded by the number of resident CTAs.
+//
+// Replaces the reference's serial token loop Stream.readBlock(with:) and InflatorOut.expand
+// (Sources/LZ77/Inflator/LZ77.InflatorBuffers.Stream.swift:266-381, LZ77.InflatorOut.swift:124-140)
+// and, for zlib streams, the running MRC32 (Sources/LZ77/Wrappers/LZ77.MRC32.swift:26-47).
+#pragma once
+
+#include "inflate_serial.cuh"
+
+namespace pngb200 {
+
+#ifndef WV_TCAP
+#define WV_TCAP 64
+#endif
+#ifndef WV_CTAS
+#define WV_CTAS 2
+#endif
+constexpr int      WV_THREADS      = 256;
+constexpr int      WV_CTAS_PER_SM  = WV_CTAS;
+constexpr int      WV_WARPS        = WV_THREADS / 32;
+constexpr uint32_t WV_SUB_BITS     = 256;
+constexpr uint32_t WV_BITS         = WV_THREADS * WV_SUB_BITS;          // 65536 bits per wave
+constexpr uint32_t WV_WORDS        = WV_BITS / 32 + 8;                  // + look-ahead for the last token
+constexpr uint32_t WV_SMEM_WORDS   = WV_WORDS + WV_WORDS / 8 + 1;
+constexpr uint32_t WV_TOKENS       = WV_TCAP;                           // staged tokens per thread
+constexpr uint32_t WV_OUT_BYTES    = 16384;                             // wave output image in smem
+constexpr uint32_t WV_BITMAP_WORDS = WV_OUT_BYTES / 32;
+constexpr uint32_t WV_LIST_CAP     = WV_BITS / 2 + 64;                  // >= copies per wave (2 bits min each)
+constexpr uint64_t WV_MAX_WAVE_OUT = (uint64_t)WV_LIST_CAP * 258;
+constexpr uint32_t WV_HDR_WORDS    = 192;                               // block header staging (<= 566 bytes)
+constexpr uint32_t ADLER_MOD32     = 65521;
+constexpr uint32_t WV_WALK_K       = 8;                                 // tokens per walk in round 0 (doubles)
+
+// cost model instrumentation (emulator builds only): loop trips per thread and per warp (max over lanes)
+#if defined(PNGB200_EMU) && defined(WV_PROFILE)
+struct WvProfile { uint64_t thread_iters[8], warp_iters[8]; };
+inline WvProfile& wv_profile() { static WvProfile p; return p; }
+inline void wv_count(int phase, uint32_t iters)
+{
+    uint32_t m = iters;
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    wv_profile().thread_iters[phase] += iters;
+    if ((threadIdx.x & 31) == 0) wv_profile().warp_iters[phase] += m;
+}
+#define WV_COUNT(phase, iters) wv_count(phase, iters)
+inline std::vector<uint16_t>& wv_walks() { static std::vector<uint16_t> v; return v; }
+#else
+#define WV_COUNT(phase, iters)
+#endif
+
+enum : uint32_t { PF_EOB = 1, PF_BAD = 2 };
+// how a thread's walk ended
+enum : uint32_t { WK_SYNC = 0, WK_END = 1, WK_EOB = 2, WK_BAD = 3, WK_OWN_EOB = 4, WK_OWN_BAD = 5, WK_RUNNING = 6 };
+
+struct WvHeader {  // block header as parsed by warp 0, broadcast to the CTA
+    int32_t  status, type, final, nlit, ndist;
+    uint32_t stored;
+    uint64_t pos;     // reader position after the header
+};
+
+struct WvShared {
+    SerialShared ser;
+    uint32_t     words[WV_SMEM_WORDS];
+    uint32_t     tok[WV_TOKENS * WV_THREADS];   // [k][t]: token k of thread t
+    uint32_t     exit_[WV_THREADS];             // where thread t's own decode left its subsequence
+    uint32_t     wpos_[WV_THREADS];             // where thread t's walk is / ended (wave-relative bit)
+    uint32_t     wn_[WV_THREADS];               // bytes produced by the walk
+    uint32_t     ovf_[WV_THREADS];              // bit position of list entry #WV_TOKENS (first one not staged)
+    uint16_t     ntok_[WV_THREADS];             // own tokens of thread t (list entries [0, ntok))
+    uint16_t     wtok_[WV_THREADS];             // walk tokens (list entries [ntok, ntok + wtok))
+    uint16_t     wc_[WV_THREADS];               // copies among the walk's tokens
+    uint8_t      kind_[WV_THREADS];             // WK_*
+    uint8_t      wlist[2][WV_THREADS];          // unfinished walks of a round, compacted
+    uint32_t     wcount[3];
+    uint32_t     bitmap[WV_BITMAP_WORDS];
+    union {                                     // the visited maps die before the image is written
+        uint8_t  outbuf[WV_OUT_BYTES + 32];
+        uint32_t mask[8 * WV_THREADS];          // [k][t]: bits 32k .. 32k+31 of subsequence t
+    } u __align__(16);
+    uint64_t     warp_sums[WV_WARPS + 1];
+    uint32_t     adler_a[WV_WARPS], adler_b[WV_WARPS];
+    uint32_t     exc[WV_WARPS], valid[WV_WARPS];
+    uint32_t     last, term, anomaly, ticket;
+    uint64_t     cyc[12], tick;                 // phase timers (thread 0)
+    WvHeader     hdr;
+};
+
+struct WvParams {
+    const StreamJob* jobs;
+    StreamResult*    results;
+    const uint32_t*  order;
+    uint32_t*        ticket;       // global work counter (zeroed before launch)
+    uint8_t*         scratch;      // per-CTA: deferred copy list + unresolved bitmap for oversized waves
+    uint64_t         scratch_stride;
+    uint64_t         bitmap_words; // size of the HBM bitmap of each CTA
+    int              count;
+};
+
+struct CopyItem { uint32_t o; uint32_t run_dist; };  // run | (dist - 1) << 16; run == 0: empty slot
+
+#ifdef PNGB200_EMU
+typedef uintptr_t saddr_t;
+inline uint32_t lds32(saddr_t addr) { return *(const uint32_t*)addr; }
+inline uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
+{
+    pos &= 0xff; len &= 0xff;   // PTX bfe.u32 semantics
+    if (len == 0 || pos > 31) return 0;
+    uint32_t v = x >> pos;
+    return len >= 32 ? v : v & ((1u << len) - 1u);
+}
+inline saddr_t smem_addr(const void* p) { return (uintptr_t)p; }
+#else
+typedef uint32_t saddr_t;
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
+{
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pos), "r"(len));
+    return r;
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#endif
+
+// register look-ahead bit reader over the staged (padded) words
+struct FastBits {
+    saddr_t  wbase;     // shared-memory address of the staged words
+    uint32_t wi;        // next word to fetch
+    uint32_t cur, nxt;
+    uint32_t off;       // < 32 at every peek
+    uint32_t pos;
+    __device__ __forceinline__ void init(saddr_t words_addr, uint32_t start)
+    {
+        wbase = words_addr;
+        const uint32_t W = start >> 5;
+        cur = lds32(wbase + ((W + (W >> 3)) << 2));
+        nxt = lds32(wbase + ((W + 1 + ((W + 1) >> 3)) << 2));
+        wi  = W + 2;
+        off = start & 31;
+        pos = start;
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, off); }
+    __device__ __forceinline__ void skip(uint32_t n)  // n <= 32
+    {
+        off += n;
+        pos += n;
+        if (off >= 32) {
+            cur = nxt;
+            nxt = lds32(wbase + ((wi + (wi >> 3)) << 2));
+            ++wi;
+            off -= 32;
+        }
+    }
+};
+
+// one table lookup of the decode passes: root entry, subtable entry behind a pointer (rare)
+template <int ROOT>
+__device__ __forceinline__ uint32_t fast_lookup(saddr_t table_addr, uint32_t bits)
+{
+    uint32_t e = lds32(table_addr + ((bits & ((1u << ROOT) - 1u)) << 2));
+    if ((e & (E_SPECIAL | E_PTR | E_INVALID)) == (E_SPECIAL | E_PTR))
+        e = lds32(table_addr + (((e >> 16) + bfe32(bits, ROOT, e_skip(e) - ROOT)) << 2));
+    return e;
+}
+
+// token word: literal = the byte; copy = 1 << 31 | (distance - 1) << 9 | run
+__device__ __forceinline__ uint32_t tok_is_copy(uint32_t tok) { return tok >> 31; }
+__device__ __forceinline__ uint32_t tok_run(uint32_t tok) { return tok & 511u; }
+__device__ __forceinline__ uint32_t tok_dist(uint32_t tok) { return ((tok >> 9) & 0x7fffu) + 1u; }
+__device__ __forceinline__ uint32_t tok_bytes(uint32_t tok) { return tok_is_copy(tok) ? tok_run(tok) : 1u; }
+
+// Decode one token at the reader's position.  Literal and copy tokens run through ONE predicated
+// body: in a warp some lanes always hold a literal while others hold a copy, so two divergent paths
+// would cost their sum every iteration.  Returns 0, PF_EOB (consumed) or PF_BAD (reader not advanced
+// past the offending code).
+__device__ __forceinline__ uint32_t wv_decode(FastBits& b, saddr_t lit, saddr_t dst, uint32_t& tok)
+{
+    const uint32_t bits = b.peek();
+    const uint32_t e = fast_lookup<LIT_ROOT>(lit, bits);
+    if (e & E_SPECIAL) {  // end of block, or an invalid code: rare, leave the loop
+        if (e & E_INVALID) return PF_BAD;
+        b.skip(e_len(e));
+        return PF_EOB;
+    }
+    const uint32_t len = e & 15u, skipn = (e >> 4) & 31u;
+    const uint32_t run = (e >> 16) + bfe32(bits, len, skipn - len);  // literals: width 0
+    b.skip(skipn);
+    const uint32_t copy = e & E_COPY;
+    const uint32_t dbits = b.peek();
+    const uint32_t d = fast_lookup<DIST_ROOT>(dst, dbits);  // ignored for literals
+    if (copy && (d & E_SPECIAL)) return PF_BAD;
+    const uint32_t dlen = d & 15u, dskip = (d >> 4) & 31u;
+    const uint32_t dist = (d >> 16) + bfe32(dbits, dlen, dskip - dlen);
+    b.skip(copy ? dskip : 0u);
+    tok = copy ? (0x80000000u | (dist - 1u) << 9 | run) : run;
+    return 0;
+}
+
+// Block headers are parsed out of a shared-memory copy of the next 768 bytes of the stream (a
+// dynamic header is at most 566 bytes), same interface as BitReader.
+struct StagedReader {
+    const uint32_t* w;
+    uint64_t        base_bit, total_bits, pos;
+    uint32_t        wi;
+    uint64_t        buf;
+    int             cnt;
+    __device__ void init(const uint32_t* words, uint64_t base, uint64_t total, uint64_t p)
+    {
+        w = words; base_bit = base; total_bits = total;
+        seek(p);
+    }
+    __device__ void seek(uint64_t p)
+    {
+        pos = p;
+        wi  = (uint32_t)((p - base_bit) >> 5);
+        buf = 0;
+        cnt = 0;
+        refill();
+        int skip = (int)(p & 31);
+        buf >>= skip;
+        cnt -= skip;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        while (cnt <= 32) {
+            buf |= (uint64_t)(wi < WV_HDR_WORDS ? w[wi] : 0u) << cnt;
+            cnt += 32;
+            ++wi;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek() const { return (uint32_t)buf; }
+    __device__ __forceinline__ void consume(int n) { buf >>= n; cnt -= n; pos += n; }
+    __device__ __forceinline__ uint32_t take(int n)
+    {
+        uint32_t v = (uint32_t)buf & (n >= 32 ? ~0u : ((1u << n) - 1u));
+        consume(n);
+        return v;
+    }
+    __device__ __forceinline__ bool have(uint64_t n) const { return pos + n <= total_bits; }
+};
+
+// ---- unresolved-byte bitmap (bit i = output byte i of the wave is not final yet) ----
+__device__ __forceinline__ uint32_t bit_mask(uint32_t lo, uint32_t hi)  // bits [lo, hi) of a word, hi <= 32
+{
+    return (hi >= 32 ? ~0u : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+}
+__device__ __forceinline__ void bits_clear(uint32_t* U, uint32_t a, uint32_t b)
+{
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    if (wa == wb) { atomicAnd(U + wa, ~bit_mask(a & 31, ((b - 1) & 31) + 1)); return; }
+    atomicAnd(U + wa, ~bit_mask(a & 31, 32));
+    for (uint32_t w = wa + 1; w < wb; ++w) atomicAnd(U + w, 0u);
+    atomicAnd(U + wb, ~bit_mask(0, ((b - 1) & 31) + 1));
+}
+__device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t a, uint32_t b)
+{
+    const volatile uint32_t* V = U;
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    uint32_t any;
+    if (wa == wb) any = V[wa] & bit_mask(a & 31, ((b - 1) & 31) + 1);
+    else {
+        any = (V[wa] & bit_mask(a & 31, 32)) | (V[wb] & bit_mask(0, ((b - 1) & 31) + 1));
+        for (uint32_t w = wa + 1; w < wb; ++w) any |= V[w];
+    }
+    __threadfence_block();
+    return any == 0;
+}
+
+// One LZ77 copy whose needed source bytes are final.  The wave's output lives at `img` (shared
+// memory image, or the HBM destination itself); sources at negative wave offsets are read from
+// HBM at `hbm` (= destination address of wave offset 0).
+__device__ __forceinline__ void lz_copy(uint8_t* img, const uint8_t* hbm, bool img_is_hbm, uint32_t o,
+                                        uint32_t run, uint32_t dist)
+{
+    const int64_t src = (int64_t)o - (int64_t)dist;
+    uint8_t*      to  = img + o;
+    if (run <= 4 && dist >= 4 && (img_is_hbm || src >= 0 || src + (int64_t)run <= 0)) {
+        // the common short copy: all loads first, then the stores
+        const uint8_t* from = (img_is_hbm || src < 0) ? hbm + src : img + src;
+        uint8_t b0 = from[0], b1 = from[1], b2 = from[2], b3 = run == 4 ? from[3] : 0;
+        to[0] = b0; to[1] = b1; to[2] = b2;
+        if (run == 4) to[3] = b3;
+        return;
+    }
+    if (img_is_hbm || src >= 0 || src + (int64_t)run <= 0) {
+        const uint8_t* from = (img_is_hbm || src < 0) ? hbm + src : img + src;
+        if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
+            uint32_t k = 0;
+            for (; k + 4 <= run; k += 4) {
+                uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
+                to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3;
+            }
+            for (; k < run; ++k) to[k] = from[k];
+        } else {
+            uint32_t q = 0;
+            for (uint32_t k = 0; k < run; ++k) {
+                to[k] = from[q];
+                if (++q == dist) q = 0;
+            }
+        }
+    } else {
+        // source starts behind the wave (HBM) and runs into the image: byte k comes from wave
+        // offset src + k; offsets < 0 are in HBM, the rest were written earlier by this loop
+        for (uint32_t k = 0; k < run; ++k) {
+            const int64_t p = src + (int64_t)k;
+            to[k] = p < 0 ? hbm[p] : img[p];
+        }
+    }
+}
+
+// per-thread emit state: where the next byte goes, which of the thread's own bytes are final
+struct EmitState {
+    uint8_t*       img;       // wave output image (shared memory, or HBM for oversized waves)
+    const uint8_t* hbm;       // HBM address of wave offset 0
+    uint32_t*      U;         // unresolved bitmap
+    CopyItem*      list;
+    uint64_t       out;       // stream offset of wave offset 0
+    uint32_t       o;         // next output byte (wave-relative)
+    uint32_t       clean;     // my bytes in [clean, o) are final
+    uint32_t       c_next;    // my next list slot
+    uint32_t       mw, mbits; // pending unresolved-bit word
+    bool           in_hbm;
+    bool           bad_ref;   // invalidStringReference seen
+};
+
+__device__ __forceinline__ void emit_token(EmitState& S, uint32_t tok)
+{
+    if (!tok_is_copy(tok)) {
+        S.img[S.o++] = (uint8_t)tok;
+        return;
+    }
+    const uint32_t run = tok_run(tok), dist = tok_dist(tok), o = S.o;
+    if ((uint64_t)dist > S.out + o) {  // invalidStringReference: the serial decoder reports it
+        S.bad_ref = true;
+        return;
+    }
+    const int64_t src = (int64_t)o - (int64_t)dist;
+    if (src + (int64_t)run <= 0 || src >= (int64_t)S.clean) {
+        // source is final: behind the wave (HBM), or inside this thread's own finished bytes
+        lz_copy(S.img, S.hbm, S.in_hbm, o, run, dist);
+    } else {
+        // flag [o, o + run) as unresolved; words are flushed once, when left
+        for (uint32_t a = o, e2 = o + run; a < e2;) {
+            const uint32_t w = a >> 5;
+            if (w != S.mw) {
+                if (S.mbits) atomicOr(S.U + S.mw, S.mbits);
+                S.mw = w;
+                S.mbits = 0;
+            }
+            const uint32_t hi = min(e2, (w + 1) << 5);
+            S.mbits |= bit_mask(a & 31, ((hi - 1) & 31) + 1);
+            a = hi;
+        }
+        S.list[S.c_next++] = CopyItem{o, run | (dist - 1) << 16};  // list is sorted by o
+        S.clean = o + run;
+    }
+    S.o = o + run;
+}
+
+// Adler-32 partial sums of bytes [0, n) at `p` for a piece whose first byte has weight `wt` (weights
+// fall by one per byte): a += sum b, bw += sum (wt - i) b_i.  64-bit accumulators, any alignment.
+__device__ __forceinline__ void adler_bytes(const uint8_t* p, uint64_t n, uint64_t wt, uint64_t& a, uint64_t& bw)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        a += p[i];
+        bw += (wt - i) * p[i];
+    }
+}
+__device__ __forceinline__ void adler_chunk16(uint4 x, uint64_t wt, uint64_t& a, uint64_t& bw)
+{
+    const uint32_t s = __vsadu4(x.x, 0) + __vsadu4(x.y, 0) + __vsadu4(x.z, 0) + __vsadu4(x.w, 0);
+    // sum (wt - i) b_i = wt * s - sum i * b_i
+    const uint32_t wsum = __dp4a(x.x, 0x03020100u, 0u) + __dp4a(x.y, 0x07060504u, 0u) +
+                          __dp4a(x.z, 0x0b0a0908u, 0u) + __dp4a(x.w, 0x0f0e0d0cu, 0u);
+    a += s;
+    bw += wt * s - wsum;
+}
+
+__global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kernel(WvParams P)
+{
+    PNGB200_DYN_SMEM(wv_smem);
+    WvShared& sh = *reinterpret_cast<WvShared*>(wv_smem);
+    const uint32_t t    = threadIdx.x;
+    const unsigned lane = lane_id(), warp = t >> 5;
+    CopyItem* const list    = reinterpret_cast<CopyItem*>(P.scratch + blockIdx.x * P.scratch_stride);
+    uint32_t* const gbitmap = reinterpret_cast<uint32_t*>(P.scratch + blockIdx.x * P.scratch_stride +
+                                                         sizeof(CopyItem) * WV_LIST_CAP);
+    for (uint32_t k = t; k < WV_BITMAP_WORDS; k += WV_THREADS) sh.bitmap[k] = 0;
+    const saddr_t words_addr = smem_addr(sh.words);
+    const saddr_t lit = smem_addr(sh.ser.lit), dstt = smem_addr(sh.ser.dist);
+
+    for (;;) {
+        __syncthreads();
+        if (t == 0) {
+            sh.ticket = atomicAdd(P.ticket, 1u);
+            sh.anomaly = 0;
+            for (int k = 0; k < 12; ++k) sh.cyc[k] = 0;
+            sh.tick = (uint64_t)clock64();
+        }
+        __syncthreads();
+        if (sh.ticket >= (uint32_t)P.count) return;
+        const int       j   = P.order ? (int)P.order[sh.ticket] : (int)sh.ticket;
+        const StreamJob job = P.jobs[j];
+        StreamResult*   r   = P.results + j;
+
+        BitReader br;
+        br.init(job.src, job.src_len, job.start_bit);
+        uint64_t out    = job.start_out;
+        uint32_t blocks = 0, waves = 0, walk_tokens = 0, resolve_rounds = 0;
+        uint64_t n_tokens = 0, n_matches = 0, n_deferred = 0;
+        int      st     = PNGB200_OK;
+        uint32_t phase  = (uint32_t)job.phase;
+        uint64_t resume_bit = job.start_bit, resume_out = job.start_out;
+        uint8_t* const dst = job.dst;
+        bool fallback = false;
+        // running Adler-32 (thread 0): valid when this launch sees the stream from its first byte
+        const bool adler_on = job.start_out == 0;
+        uint32_t   s1 = 1, s2 = 0;
+        uint64_t   pend_len = 0;       // a finished piece whose partial sums wait in sh.adler_*
+        bool       pend = false;
+        // fold the pending piece into (s1, s2): called by every thread right after a barrier
+        auto fold_adler = [&]() {
+            if (pend && t == 0) {
+                uint64_t A = 0, B = 0;
+                for (int w = 0; w < WV_WARPS; ++w) { A += sh.adler_a[w]; B += sh.adler_b[w]; }
+                s2 = (uint32_t)((s2 + (pend_len % ADLER_MOD32) * s1 + B) % ADLER_MOD32);
+                s1 = (uint32_t)((s1 + A) % ADLER_MOD32);
+            }
+            pend = false;
+        };
+        // CTA-wide partial sums of a finished piece of `n` bytes at HBM address `p` (stored blocks,
+        // oversized waves); every thread calls it, results land in sh.adler_* for the next fold
+        auto adler_hbm = [&](const uint8_t* p, uint64_t n) {
+            uint64_t a = 0, bw = 0;
+            const uint64_t per = (n + WV_THREADS - 1) / WV_THREADS;
+            const uint64_t lo = min((uint64_t)t * per, n), hi = min(lo + per, n);
+            adler_bytes(p + lo, hi - lo, n - lo, a, bw);
+            uint32_t a32 = (uint32_t)(a % ADLER_MOD32), b32 = (uint32_t)(bw % ADLER_MOD32);
+            for (int o = 16; o; o >>= 1) {
+                a32 += __shfl_down_sync(0xffffffffu, a32, o);
+                b32 += __shfl_down_sync(0xffffffffu, b32, o);
+            }
+            if (lane == 0) { sh.adler_a[warp] = a32; sh.adler_b[warp] = b32; }
+            pend = true;
+            pend_len = n;
+        };
+
+        // phase timer: thread 0 charges the cycles since the last tick to phase `i`
+        auto tick = [&](int i) {
+            if (t == 0) {
+                const uint64_t now = (uint64_t)clock64();
+                sh.cyc[i] += now - sh.tick;
+                sh.tick = now;
+            }
+        };
+
+        if (phase == 0) {
+            st = read_stream_header(br, job.format, r);
+            if (st == PNGB200_OK) {
+                resume_bit = br.at();
+                phase = 1;
+            }
+        }
+        if (st == PNGB200_OK && phase == 2) st = read_trailer(br, job.format, r);
+
+        while (st == PNGB200_OK && phase == 1) {
+            // warp 0 walks the header bits alone; the CTA then builds the tables together
+            __syncthreads();
+            fold_adler();
+            {
+                const uint64_t hbase = br.pos >> 5;
+                for (uint32_t k = t; k < WV_HDR_WORDS; k += WV_THREADS) sh.words[k] = br.load_word(hbase + k);
+                __syncthreads();
+                if (warp == 0) {
+                    int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
+                    uint32_t stored0 = 0;
+                    StagedReader sr;
+                    sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
+                    int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
+                    if (lane == 0) sh.hdr = WvHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                }
+            }
+            __syncthreads();
+            const WvHeader hdr = sh.hdr;
+            st = hdr.status;
+            if (st != PNGB200_OK) break;
+            const int      type = hdr.type, final = hdr.final;
+            const uint32_t stored = hdr.stored;
+            br.seek(hdr.pos);
+            if (type != 0) {
+                st = build_block_tables(&sh.ser, r, hdr.nlit, hdr.ndist, (int)t, WV_THREADS);
+                if (st != PNGB200_OK) break;
+            }
+            tick(0);
+            if (type == 0) {
+                if (!br.have(8 * (uint64_t)stored)) { st = PNGB200_NEED_MORE_INPUT; break; }
+                if (out + stored > job.dst_cap) { st = fail(r, PNGB200_ERR_OUTPUT_CAPACITY); break; }
+                const uint8_t* s = job.src + (br.at() >> 3);
+                for (uint32_t k = t; k < stored; k += WV_THREADS) dst[out + k] = s[k];
+                if (adler_on && stored) adler_hbm(s, stored);
+                out += stored;
+                br.seek(br.pos + 8 * (uint64_t)stored);
+                __syncthreads();
+                fold_adler();
+                tick(9);
+            } else {
+                bool block_done = false;
+                while (!block_done) {
+                    ++waves;
+                    // ---- stage the wave's bits in shared memory ----
+                    const uint64_t wstart = br.pos;                       // absolute bit (reader space)
+                    const uint64_t wbase  = (wstart >> 5) & ~(uint64_t)7; // first staged word
+                    __syncthreads();
+                    for (uint32_t k = t; k < WV_WORDS; k += WV_THREADS)
+                        sh.words[k + (k >> 3)] = br.load_word(wbase + k);
+                    __syncthreads();                                      // (1)
+                    fold_adler();
+                    tick(1);
+                    const uint32_t rel0  = (uint32_t)(wstart - (wbase << 5));  // < 256
+                    const uint32_t base  = t * WV_SUB_BITS;
+                    const uint32_t limit = base + WV_SUB_BITS;
+                    uint32_t* const mk = sh.u.mask;
+
+                    // ---- A. speculative decode of my subsequence ----
+                    uint32_t n = 0, nout = 0, ncopy = 0, flags = 0, exit_bit;
+                    {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) mk[k * WV_THREADS + t] = 0;
+                        FastBits b;
+                        b.init(words_addr, t == 0 ? rel0 : base);
+                        uint32_t mi = 0, mw = 0;
+                        while (b.pos < limit) {
+                            const uint32_t rr = b.pos - base, wi = rr >> 5;
+                            if (wi != mi) {
+                                mk[mi * WV_THREADS + t] = mw;
+                                mw = 0;
+                                mi = wi;
+                            }
+                            mw |= 1u << (rr & 31);
+                            uint32_t tok = 0;
+                            const uint32_t s = wv_decode(b, lit, dstt, tok);
+                            if (s) { flags = s; break; }
+                            if (n < WV_TOKENS) sh.tok[n * WV_THREADS + t] = tok;
+                            else if (n == WV_TOKENS) sh.ovf_[t] = base + rr;   // where list entry #WV_TOKENS starts
+                            ++n;
+                            nout += tok_bytes(tok);
+                            ncopy += tok_is_copy(tok);
+                        }
+                        mk[mi * WV_THREADS + t] = mw;
+                        exit_bit = b.pos;
+                    }
+                    sh.ntok_[t] = (uint16_t)n;
+                    sh.exit_[t] = exit_bit;
+                    if (t == 0) sh.wcount[0] = 0;
+                    WV_COUNT(0, n);
+                    __syncthreads();                                      // (2) maps complete
+                    tick(2);
+
+                    // ---- B. walks: from each exit until the walk joins a subsequence owner's decode.  Walk
+                    //      lengths are heavy-tailed (median 6 tokens, 1 % beyond 40), so they run in rounds of
+                    //      8, 16, 32 ... tokens; the unfinished walks of a round are compacted onto the lowest
+                    //      threads (state in shared memory), so that a round costs what it still has to do ----
+                    {
+                        uint32_t u = t, pos = exit_bit, wn = 0, wc = 0, wtok = 0;
+                        bool     active = flags == 0;
+                        if (!active) {
+                            sh.kind_[t] = (uint8_t)(flags == PF_EOB ? WK_OWN_EOB : WK_OWN_BAD);
+                            sh.wpos_[t] = exit_bit;
+                            sh.wn_[t] = 0;
+                            sh.wc_[t] = 0;
+                            sh.wtok_[t] = 0;
+                        }
+                        for (uint32_t round = 0;; ++round) {
+                            const uint32_t K = WV_WALK_K << min(round, 6u);
+                            bool     still = false;
+                            uint32_t iters = 0;
+                            if (active) {
+                                const uint32_t nu = sh.ntok_[u];
+                                FastBits b;
+                                b.init(words_addr, pos);
+                                uint32_t kind = WK_RUNNING;
+                                for (; iters < K; ++iters) {
+                                    const uint32_t p = b.pos;
+                                    if (p >= WV_BITS) { kind = WK_END; break; }
+                                    const uint32_t s = p >> 8, rr = p & 255u;
+                                    if ((mk[(rr >> 5) * WV_THREADS + s] >> (rr & 31)) & 1u) { kind = WK_SYNC; break; }
+                                    uint32_t tok = 0;
+                                    const uint32_t e = wv_decode(b, lit, dstt, tok);
+                                    if (e) { kind = e == PF_EOB ? WK_EOB : WK_BAD; break; }
+                                    // the walk's tokens continue the list of the thread it started from
+                                    const uint32_t slot = nu + wtok;
+                                    if (slot < WV_TOKENS) sh.tok[slot * WV_THREADS + u] = tok;
+                                    else if (slot == WV_TOKENS) sh.ovf_[u] = p;
+                                    wn += tok_bytes(tok);
+                                    wc += tok_is_copy(tok);
+                                    ++wtok;
+                                }
+                                sh.wpos_[u] = b.pos;
+                                sh.wn_[u]   = wn;
+                                sh.wc_[u]   = (uint16_t)wc;
+                                sh.wtok_[u] = (uint16_t)wtok;
+                                sh.kind_[u] = (uint8_t)kind;
+                                still = kind == WK_RUNNING;
+                            }
+                            WV_COUNT(1, iters);
+                            if (t == 0) sh.wcount[(round + 1) % 3] = 0;
+                            const unsigned bal = __ballot_sync(0xffffffffu, still);
+                            if (still) {
+                                uint32_t at = 0;
+                                const int leader = __ffs((int)bal) - 1;
+                                if ((int)lane == leader) at = atomicAdd(&sh.wcount[round % 3], (uint32_t)__popc(bal));
+                                at = __shfl_sync(bal, at, leader);
+                                sh.wlist[round & 1][at + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)u;
+                            }
+                            __syncthreads();
+                            const uint32_t cnt = sh.wcount[round % 3];
+                            if (cnt == 0) break;
+                            active = t < cnt;
+                            if (active) {
+                                u    = sh.wlist[round & 1][t];
+                                pos  = sh.wpos_[u];
+                                wn   = sh.wn_[u];
+                                wc   = sh.wc_[u];
+                                wtok = sh.wtok_[u];
+                            }
+                        }
+                    }
+                    tick(3);
+                    const uint32_t kind = sh.kind_[t], wpos = sh.wpos_[t];
+#if defined(PNGB200_EMU) && defined(WV_PROFILE)
+                    wv_walks().push_back((uint16_t)sh.wtok_[t]);
+                    wv_walks().push_back((uint16_t)n);
+                    wv_walks().push_back((uint16_t)t);
+#endif
+                    {
+                        const unsigned e = __ballot_sync(0xffffffffu, !(kind == WK_SYNC && (wpos >> 8) == t + 1));
+                        if (lane == 0) sh.exc[warp] = e;
+                    }
+                    __syncthreads();                                      // (3)
+
+                    // ---- C. the true chain: orbit of thread 0 (one thread, steps only at exceptions) ----
+                    if (t == 0) {
+                        uint32_t V[WV_WARPS];
+#pragma unroll
+                        for (int w = 0; w < WV_WARPS; ++w) V[w] = 0;
+                        uint32_t cur = 0, x = 0;
+                        for (;;) {
+                            uint32_t w = cur >> 5, m = sh.exc[w] & (~0u << (cur & 31));
+                            while (m == 0) m = sh.exc[++w];   // thread 255 never joins anybody: always found
+                            x = w * 32 + (uint32_t)__ffs((int)m) - 1;
+                            // threads cur .. x are on the chain
+                            for (uint32_t a = cur; a <= x;) {
+                                const uint32_t vw = a >> 5, hi = min(x + 1, (vw + 1) << 5);
+#pragma unroll
+                                for (int q = 0; q < WV_WARPS; ++q)
+                                    if (q == (int)vw) V[q] |= bit_mask(a & 31, ((hi - 1) & 31) + 1);
+                                a = hi;
+                            }
+                            if (sh.kind_[x] != WK_SYNC) break;
+                            cur = sh.wpos_[x] >> 8;   // > x + 1: the walk crossed subsequences without joining
+                        }
+#pragma unroll
+                        for (int w = 0; w < WV_WARPS; ++w) sh.valid[w] = V[w];
+                        sh.last = x;
+                        sh.term = sh.kind_[x];
+                    }
+                    __syncthreads();                                      // (4)
+                    tick(4);
+
+                    // ---- D. my share of the chain: the tokens that START in my subsequence = the walk of my
+                    //      predecessor on the chain (up to the position where it joined me) + my own tokens from
+                    //      there on; the last thread of the chain adds its own walk ----
+                    const bool     on_chain = (sh.valid[warp] >> lane) & 1u;
+#if defined(PNGB200_EMU) && defined(WV_PROFILE)
+                    wv_walks()[wv_walks().size() - 3 * (WV_THREADS - t) + 2] = (uint16_t)on_chain;
+#endif
+                    const uint32_t last = sh.last, term = sh.term;
+                    uint32_t k0 = 0, p0 = rel0;      // index / position of my first valid token
+                    uint32_t pred = 0, pw = 0;       // predecessor on the chain, tokens of its walk
+                    uint32_t my_nout = 0, my_ncopy = 0;
+                    if (on_chain) {
+                        uint32_t pn = 0, pc = 0;
+                        if (t > 0) {
+                            uint32_t w = warp, m = sh.valid[w] & ((1u << lane) - 1u);
+                            while (m == 0) m = sh.valid[--w];
+                            pred = w * 32 + 31 - (uint32_t)__clz((int)m);
+                            p0 = sh.wpos_[pred];
+                            pw = sh.wtok_[pred];
+                            pn = sh.wn_[pred];
+                            pc = sh.wc_[pred];
+                            const uint32_t rr = p0 - base, full = rr >> 5;
+                            for (uint32_t q = 0; q < full; ++q) k0 += (uint32_t)__popc(mk[q * WV_THREADS + t]);
+                            k0 += (uint32_t)__popc(mk[full * WV_THREADS + t] & ((1u << (rr & 31)) - 1u));
+                        }
+                        uint32_t pre_n = 0, pre_c = 0;
+                        const uint32_t kk = min(k0, min(n, WV_TOKENS));
+                        for (uint32_t i = 0; i < kk; ++i) {
+                            const uint32_t tok = sh.tok[i * WV_THREADS + t];
+                            pre_n += tok_bytes(tok);
+                            pre_c += tok_is_copy(tok);
+                        }
+                        if (k0 > WV_TOKENS) {  // joined behind the staged tokens: count the rest of the prefix
+                            FastBits b;
+                            b.init(words_addr, sh.ovf_[t]);
+                            while (b.pos != p0 && b.pos < limit) {
+                                uint32_t tok = 0;
+                                if (wv_decode(b, lit, dstt, tok)) break;
+                                pre_n += tok_bytes(tok);
+                                pre_c += tok_is_copy(tok);
+                            }
+                        }
+                        my_nout  = pn + nout - pre_n;
+                        my_ncopy = pc + ncopy - pre_c;
+                        if (t == last) {
+                            my_nout += sh.wn_[t];
+                            my_ncopy += sh.wc_[t];
+                            // ---- anomalies on the chain -> serial decoder ----
+                            if (term == WK_BAD || term == WK_OWN_BAD || (wbase << 5) + wpos > br.total_bits)
+                                sh.anomaly = 1;
+                        }
+                    }
+                    // ---- scan of output byte counts and copy counts (packed: copies << 40 | bytes) ----
+                    const uint64_t mine = (uint64_t)my_ncopy << 40 | my_nout;
+                    uint64_t incl = mine;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += v;
+                    }
+                    if (lane == 31) sh.warp_sums[warp] = incl;
+                    __syncthreads();                                      // (5)
+                    if (warp == 0) {
+                        uint64_t ws = lane < WV_WARPS ? sh.warp_sums[lane] : 0, wi = ws;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            uint64_t v = __shfl_up_sync(0xffffffffu, wi, o);
+                            if ((int)lane >= o) wi += v;
+                        }
+                        if (lane < WV_WARPS) sh.warp_sums[lane] = wi - ws;  // exclusive
+                        if (lane == WV_WARPS - 1) sh.warp_sums[WV_WARPS] = wi;  // wave totals
+                    }
+                    __syncthreads();                                      // (6) maps are dead from here
+                    tick(5);
+                    const uint64_t excl    = sh.warp_sums[warp] + incl - mine;
+                    const uint32_t o_start = (uint32_t)(excl & 0xffffffffffull);
+                    const uint32_t c_start = (uint32_t)(excl >> 40);           // my first list slot
+                    const uint32_t total   = (uint32_t)(sh.warp_sums[WV_WARPS] & 0xffffffffffull);
+                    const uint32_t np      = (uint32_t)(sh.warp_sums[WV_WARPS] >> 40);
+                    if (sh.anomaly || out + total > job.dst_cap || total > P.bitmap_words * 32) {
+                        fallback = true;
+                        break;
+                    }
+                    // ---- E. emit: replay my staged tokens, decode my walk segment ----
+                    uint8_t* const  wdst   = dst + out;           // HBM address of wave offset 0
+                    const uint32_t  shift  = (uint32_t)((uintptr_t)wdst & 15);
+                    const bool      in_hbm = total > WV_OUT_BYTES;
+                    uint8_t* const  img    = in_hbm ? wdst : sh.u.outbuf + shift;
+                    uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
+                    uint32_t deferred = 0;
+                    uint32_t replayed = 0, redone = 0;
+                    if (on_chain) {
+                        EmitState S;
+                        S.img = img; S.hbm = wdst; S.U = U; S.list = list; S.out = out;
+                        S.o = o_start; S.clean = o_start; S.c_next = c_start;
+                        S.mw = o_start >> 5; S.mbits = 0; S.in_hbm = in_hbm; S.bad_ref = false;
+                        // entries [a, b) of thread u's token list, covering the bits [from, to) of the wave
+                        auto emit_segment = [&](uint32_t u, uint32_t a, uint32_t b, uint32_t from, uint32_t to) {
+                            const uint32_t kend = min(b, WV_TOKENS);
+                            for (uint32_t k = a; k < kend; ++k) emit_token(S, sh.tok[k * WV_THREADS + u]);
+                            replayed += kend > a ? kend - a : 0;
+                            if (b > WV_TOKENS) {
+                                // what did not fit the staging area is decoded again (rare: > WV_TOKENS tokens
+                                // in 256 bits + walk)
+                                FastBits bb;
+                                bb.init(words_addr, a > WV_TOKENS ? from : sh.ovf_[u]);
+                                while (bb.pos != to && bb.pos < WV_BITS + 64) {
+                                    uint32_t tok = 0;
+                                    if (wv_decode(bb, lit, dstt, tok)) break;
+                                    emit_token(S, tok);
+                                    ++redone;
+                                }
+                            }
+                        };
+                        if (pw) {
+                            const uint32_t a = sh.ntok_[pred];
+                            emit_segment(pred, a, a + pw, sh.exit_[pred], p0);
+                        }
+                        emit_segment(t, k0, n, p0, exit_bit);
+                        if (t == last && sh.wtok_[t]) emit_segment(t, n, n + sh.wtok_[t], exit_bit, wpos);
+                        if (S.mbits) atomicOr(U + S.mw, S.mbits);
+                        if (S.bad_ref) sh.anomaly = 1;
+                        deferred = S.c_next - c_start;
+                        for (uint32_t c = S.c_next; c < c_start + my_ncopy; ++c) list[c] = CopyItem{0, 0};
+                    }
+#if defined(PNGB200_EMU) && defined(WV_PROFILE)
+                    wv_walks()[wv_walks().size() - 3 * (WV_THREADS - t) + 1] = (uint16_t)replayed;
+#endif
+                    WV_COUNT(2, replayed);
+                    WV_COUNT(3, redone);
+                    __threadfence_block();
+                    __syncthreads();                                      // (7)
+                    tick(6);
+                    // ---- F. resolve: no CTA barriers.  The list is sorted by output offset and a copy only
+                    //      depends on smaller offsets, so a lane may simply block on its current item
+                    //      (items t, t + 256, ... in order): the smallest open item is always ready ----
+                    if (!sh.anomaly && np) {
+                        // the list lives in L2: the item after the current one is fetched while the current
+                        // one is being copied
+                        uint32_t idx  = t, rounds = 0;
+                        CopyItem it   = CopyItem{0, 0}, nxt = CopyItem{0, 0};
+                        bool     have = false, have_nxt = false;
+                        if (idx < np) {
+                            nxt = list[idx];
+                            idx += WV_THREADS;
+                            have_nxt = true;
+                        }
+                        for (;;) {
+                            if (!have && have_nxt) {
+                                it = nxt;
+                                have = (it.run_dist & 0xffff) != 0;   // empty slot: the copy ran inline
+                                have_nxt = idx < np;
+                                if (have_nxt) {
+                                    nxt = list[idx];
+                                    idx += WV_THREADS;
+                                }
+                            }
+                            bool progressed = false;
+                            if (have) {
+                                const uint32_t run = it.run_dist & 0xffff, dist = (it.run_dist >> 16) + 1;
+                                const int64_t  src = (int64_t)it.o - (int64_t)dist;
+                                const int64_t  hi  = src + (int64_t)min(run, dist);
+                                bool ready = true;
+                                if (hi > 0) ready = bits_all_clear(U, (uint32_t)max(src, (int64_t)0), (uint32_t)hi);
+                                if (ready) {
+                                    lz_copy(img, wdst, in_hbm, it.o, run, dist);
+                                    __threadfence_block();
+                                    bits_clear(U, it.o, it.o + run);
+                                    have = false;
+                                    progressed = true;
+                                }
+                            }
+                            ++resolve_rounds;
+                            ++rounds;
+                            if (!__any_sync(0xffffffffu, have || have_nxt)) break;
+                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(40);
+                        }
+                        WV_COUNT(4, rounds);
+                    }
+                    __threadfence_block();
+                    __syncthreads();                                      // (8)
+                    tick(7);
+                    if (sh.anomaly) {
+                        // leave the bitmap clean for whoever uses it next
+                        for (uint32_t k = t; k < (total + 31) / 32; k += WV_THREADS) U[k] = 0;
+                        fallback = true;
+                        break;
+                    }
+                    // ---- G. store: shared-memory image -> HBM, 16-byte coalesced; Adler-32 partial sums ----
+                    if (!in_hbm && total) {
+                        uint8_t* const       gbase = wdst - shift;           // 16-byte aligned
+                        const uint32_t       end   = shift + total;          // bytes [shift, end) are ours
+                        const uint32_t       nq    = (end + 15) >> 4;
+                        const uint4* const   q     = reinterpret_cast<const uint4*>(sh.u.outbuf);
+                        uint64_t a = 0, bw = 0;
+                        for (uint32_t c = t; c < nq; c += WV_THREADS) {
+                            const uint32_t lo = c << 4, hi = lo + 16;
+                            if (lo >= shift && hi <= end) {
+                                const uint4 x = q[c];
+                                reinterpret_cast<uint4*>(gbase)[c] = x;
+                                adler_chunk16(x, end - lo, a, bw);
+                            } else {
+                                for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) {
+                                    const uint8_t v = sh.u.outbuf[k];
+                                    gbase[k] = v;
+                                    a += v;
+                                    bw += (uint64_t)(end - k) * v;
+                                }
+                            }
+                        }
+                        if (adler_on) {
+                            uint32_t a32 = (uint32_t)a, b32 = (uint32_t)(bw % ADLER_MOD32);
+                            for (int o = 16; o; o >>= 1) {
+                                a32 += __shfl_down_sync(0xffffffffu, a32, o);
+                                b32 += __shfl_down_sync(0xffffffffu, b32, o);
+                            }
+                            if (lane == 0) { sh.adler_a[warp] = a32; sh.adler_b[warp] = b32; }
+                            pend = true;
+                            pend_len = total;
+                        }
+                    } else if (in_hbm && adler_on) {
+                        adler_hbm(wdst, total);
+                    }
+                    tick(8);
+                    out += total;
+                    walk_tokens += sh.wtok_[t];
+                    if (t == 0) { n_matches += np; }
+                    n_tokens += replayed + redone;
+                    n_deferred += deferred;
+                    br.seek((wbase << 5) + sh.wpos_[last]);
+                    if (term == WK_EOB || term == WK_OWN_EOB) block_done = true;
+                }
+                if (fallback) break;
+            }
+            ++blocks;
+            resume_bit = br.at();
+            resume_out = out;
+            if (final) {
+                phase = 2;
+                st = read_trailer(br, job.format, r);
+                break;
+            }
+        }
+        __syncthreads();
+        fold_adler();
+        // per-stream statistics (the reference's -DDUMP_LZ77_BLOCKS style counters): CTA sums
+        {
+            uint64_t v0 = n_tokens, v1 = n_deferred;
+            uint32_t v2 = walk_tokens, v3 = resolve_rounds;
+            for (int o = 16; o; o >>= 1) {
+                v0 += __shfl_down_sync(0xffffffffu, v0, o);
+                v1 += __shfl_down_sync(0xffffffffu, v1, o);
+                v2 += __shfl_down_sync(0xffffffffu, v2, o);
+                v3 = max(v3, __shfl_down_sync(0xffffffffu, v3, o));
+            }
+            if (lane == 0) {
+                sh.warp_sums[warp] = v0;
+                sh.adler_a[warp] = (uint32_t)min(v1, (uint64_t)0xffffffffu);
+                sh.adler_b[warp] = v2;
+            }
+            __syncthreads();
+            if (t == 0) {
+                uint64_t tk = 0, df = 0, wt = 0;
+                for (int w = 0; w < WV_WARPS; ++w) { tk += sh.warp_sums[w]; df += sh.adler_a[w]; wt += sh.adler_b[w]; }
+                r->stat_waves          = waves;
+                r->stat_sync_rounds    = (uint32_t)wt;          // tokens decoded by walks
+                r->stat_resolve_rounds = v3;
+                r->stat_tokens         = tk;
+                r->stat_matches        = n_matches;
+                r->stat_deferred       = df;
+                for (int k = 0; k < 12; ++k) r->stat_cycles[k] = sh.cyc[k];
+            }
+        }
+        if (fallback) {
+            // the serial decoder redoes this block (and whatever follows) and owns the result record
+            __syncthreads();
+            if (warp == 0) serial_inflate(sh.ser, job, r, resume_bit, resume_out, 1, blocks);
+        } else if (t == 0) {
+            if (r->status == 0) r->status = st;
+            r->produced      = out;
+            r->consumed_bits = br.at();
+            r->blocks        = blocks;
+            r->resume_bit    = resume_bit;
+            r->resume_out    = resume_out;
+            r->phase         = phase;
+            if (adler_on && job.format != PNGB200_FORMAT_GZIP) {
+                // LZ77.InflatorBuffers.advance(.checksum): compare with the trailer (InflatorBuffers.swift:109-130)
+                const uint32_t computed = s2 << 16 | s1;
+                r->checksum = computed;
+                r->ck_done  = 1;
+                if (r->trailer_seen && job.format != PNGB200_FORMAT_IOS && r->status >= 0 && r->declared != computed) {
+                    r->status = PNGB200_ERR_STREAM_CHECKSUM;
+                    r->err_a  = r->declared;
+                    r->err_b  = computed;
+                }
+            }
+        }
+        if (t == 0) r->stat_fallback = fallback ? 1u : 0u;
+    }
+}
+
+#ifndef PNGB200_EMU
+// host side: opt in to the large dynamic shared memory on the current device (once per context)
+inline int configure_inflate_wave()
+{
+    return (int)cudaFuncSetAttribute(inflate_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(WvShared));
+}
+#endif
+
+inline uint64_t wv_bitmap_words(uint64_t max_dst_cap)
+{
+    uint64_t bytes = max_dst_cap < WV_MAX_WAVE_OUT ? max_dst_cap : WV_MAX_WAVE_OUT;
+    return (bytes + 31) / 32 + 8;
+}
+inline uint64_t wv_scratch_stride(uint64_t bitmap_words)
+{
+    uint64_t s = sizeof(CopyItem) * (uint64_t)WV_LIST_CAP + 4 * bitmap_words;
+    return (s + 255) / 256 * 256;
+}
+
+}  // namespace pngb200

@@ -20,7 +20,7 @@
 #include "filter.cuh"
 #include "color.cuh"
 #include "crc32.cuh"
-#include "inflate_parallel.cuh"
+#include "inflate_wave.cuh"
 #include "inflate_serial.cuh"
 #include "unfilter.cuh"
 
@@ -192,10 +192,10 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
         if (!par.empty()) {
             uint64_t max_cap = 0;
             for (uint32_t i : par) max_cap = std::max<uint64_t>(max_cap, h_jobs[i].dst_cap);
-            ParParams pp;
-            pp.bitmap_words = par_bitmap_words(max_cap);
-            pp.scratch_stride = par_scratch_stride(pp.bitmap_words);
-            unsigned grid = (unsigned)std::min<size_t>(par.size(), (size_t)ctx->sm_count * PAR_CTAS_PER_SM);
+            WvParams pp;
+            pp.bitmap_words = wv_bitmap_words(max_cap);
+            pp.scratch_stride = wv_scratch_stride(pp.bitmap_words);
+            unsigned grid = (unsigned)std::min<size_t>(par.size(), (size_t)ctx->sm_count * WV_CTAS_PER_SM);
             size_t need = (size_t)pp.scratch_stride * grid + 256;
             // The per-CTA "unresolved" bitmaps must be all-zero when a launch starts; the kernel
             // leaves them clean.  A different stride moves the bitmaps onto bytes that held copy
@@ -214,7 +214,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             pp.count = (int)par.size();
             if (int rc = before_first_launch()) return rc;
             hooked = true;
-            inflate_parallel_kernel<<<grid, PAR_THREADS, sizeof(ParShared), ctx->stream>>>(pp);
+            inflate_wave_kernel<<<grid, WV_THREADS, sizeof(WvShared), ctx->stream>>>(pp);
             ctx->launches++;
         }
         if (!hooked)
@@ -482,8 +482,8 @@ pngb200_ctx* pngb200_ctx_create(int device)
         delete ctx;
         return nullptr;
     }
-    if (configure_inflate_parallel() != 0) {
-        set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(ParShared));
+    if (configure_inflate_wave() != 0) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(WvShared));
         delete ctx;
         return nullptr;
     }
@@ -549,6 +549,25 @@ int pngb200_ctx_inflate_stats(pngb200_ctx* ctx, size_t count, uint64_t out[4])
         out[1] += r[i].stat_sync_rounds;
         out[2] += r[i].stat_resolve_rounds;
         out[3] += r[i].stat_fallback;
+    }
+    return PNGB200_OK;
+}
+
+int pngb200_ctx_inflate_counters(pngb200_ctx* ctx, size_t count, uint64_t out[24])
+{
+    if (!ctx || !out || ctx->h_results.cap < sizeof(StreamResult) * count) return PNGB200_ERR_BAD_ARGUMENT;
+    const StreamResult* r = ctx->h_results.as<StreamResult>();
+    for (int k = 0; k < 24; ++k) out[k] = 0;
+    for (size_t i = 0; i < count; ++i) {
+        out[0] += r[i].stat_waves;
+        out[1] += r[i].stat_sync_rounds;
+        out[2] += r[i].stat_resolve_rounds;
+        out[3] += r[i].stat_fallback;
+        out[4] += r[i].stat_tokens;
+        out[5] += r[i].stat_matches;
+        out[6] += r[i].stat_deferred;
+        out[7] += r[i].blocks;
+        for (int k = 0; k < 12; ++k) out[8 + k] += r[i].stat_cycles[k];
     }
     return PNGB200_OK;
 }
