@@ -2,60 +2,62 @@
 //
 // One CTA of 256 threads eats a DEFLATE block in WAVES of 256 subsequences x 256 bits (8 KiB of
 // compressed data staged in shared memory, padded 9/8 so lane-strided word reads do not conflict).
+// The last 32 KiB of output -- the LZ77 window -- and the wave's own output live in a 64 KiB RING in
+// shared memory (index = stream offset mod 65536), so no token of a wave ever waits for HBM: literals,
+// window copies and the unresolved-copy sweep are shared-memory traffic; HBM sees the compressed words
+// once (coalesced) and the output once (16-byte coalesced stores out of the ring).
+//
 // DEFLATE has no sync markers, but Huffman codes self-synchronise: a decoder started at a wrong bit
-// falls into step with the true token sequence after a few tokens.  Round 1 exploited that with
-// CTA-wide re-decode rounds (3.2 decode passes per bit, ~12 barriers per wave).  Here every bit is
-// decoded about 1.2 times and a wave costs 8 barriers:
+// falls into step with the true token sequence after a few tokens (median 6, 1 % beyond 40 for PNG
+// data).  Round 1 exploited that with CTA-wide re-decode rounds (3.2 decode passes per bit, ~20
+// barriers per wave).  Here:
 //
 //   A. speculate  thread t decodes subsequence t from a guessed start (thread 0's is exact) until it
-//                 leaves the subsequence.  It records (i) a 256-bit map of the token start positions
-//                 it visited, (ii) the tokens themselves (<= WV_TCAP per thread, 32-bit: literal
-//                 byte, or run | distance), (iii) byte/copy totals, (iv) its exit position.
-//   B. walk       thread t continues from ITS exit position through the following subsequences until
-//                 it lands on a position the owner of that subsequence also visited (from there on
-//                 the two decodes are identical), or on end-of-block / the end of the wave.  Usually
-//                 a handful of tokens.
-//   C. resolve    the true token chain is the orbit of thread 0 under "t -> subsequence where t's
-//                 walk joined".  One thread follows it, jumping over the (rare) subsequences a walk
-//                 crossed without joining.  Every thread on the chain owns the chain segment from
-//                 the position where its predecessor joined it to the position where its own walk
-//                 joined the next one; the index of its first valid token is a popcount of its map.
-//   D. count      bytes / copies of the owned segment = totals - the garbage prefix (read back from
-//                 the staged tokens) + the walk's counts; CTA scan -> output offsets, list slots.
-//   E. emit       staged tokens are replayed (no Huffman decoding); only the short walk segment is
-//                 decoded again.  Literals go to a 16 KiB shared-memory image of the wave's output.
-//                 An LZ77 copy runs immediately when its source is final: behind the wave (already
-//                 in HBM -- in PNG the distance is about one scanline) or inside the thread's own
-//                 finished bytes (distance of a pixel or two).  Only copies that read another
-//                 thread's bytes of THIS wave are deferred to a list sorted by output offset, their
-//                 destination bytes flagged in an "unresolved" bitmap.
+//                 leaves the subsequence.  It records a 256-bit map of the token start positions it
+//                 visited, byte / copy counts at every 32-bit boundary of the map, and its exit position.
+//   B. walk       a walk continues from each exit through the following subsequences until it lands on
+//                 a position the owner of that subsequence also visited (from there on the two decodes
+//                 are identical), or on end-of-block / the end of the wave.  Walk lengths are heavy
+//                 tailed, so walks run in rounds of 8, 16, 32 ... tokens and the unfinished ones are
+//                 compacted onto the lowest threads: a round costs what it still has to do.
+//   C. chain      the true token chain is the orbit of thread 0 under "t -> subsequence where t's walk
+//                 joined".  One thread follows it in registers, stepping only where a walk crossed a
+//                 subsequence without joining.
+//   D. count      a thread on the chain owns the tokens that START in its subsequence: from its
+//                 predecessor's exit to its own exit.  Their byte / copy counts = the predecessor's walk
+//                 + own totals - the garbage prefix (checkpoint + at most 31 bits decoded again);
+//                 CTA scan -> output offsets and list slots.
+//   E. emit       every thread decodes its share once more and writes it: literals into the ring; an
+//                 LZ77 copy runs immediately when its source is final -- behind the wave (the window:
+//                 in PNG the distance is about one scanline) or inside the thread's own finished bytes
+//                 (distance of a pixel or two).  Only copies that read another thread's bytes of THIS
+//                 wave are deferred to a list sorted by output offset, their destination bytes flagged
+//                 in an "unresolved" bitmap.
 //   F. resolve    barrier-free sweep of the deferred list (a copy runs once none of its source bytes
 //                 is flagged; the smallest open item is always ready).
-//   G. store      image -> HBM with 16-byte coalesced stores; the Adler-32 of the wave is taken from
+//   G. store      ring -> HBM with 16-byte coalesced stores; the Adler-32 of the wave is taken from
 //                 the same registers (reassociated sums, folded per wave), so zlib streams need no
 //                 separate checksum pass over the inflated bytes.
 //
-// Waves that expand beyond the image (flat graphics: 8 KiB -> megabytes) write HBM directly and keep
-// their bitmap in HBM scratch.  Anything irregular (invalid symbol on the chain, truncation, output
-// overflow, distance before the start of the output) is not handled here: warp 0 re-runs the block
-// with the serial decoder (inflate_serial.cuh), which owns the exact error semantics of the
-// reference.
+// Waves that expand beyond 32 KiB (flat graphics: 8 KiB -> megabytes) write HBM directly, read their
+// sources from HBM and keep their bitmap in HBM scratch; the ring is refilled from HBM afterwards.
+// Anything irregular (invalid symbol on the chain, truncation, output overflow, distance before the
+// start of the output) is not handled here: warp 0 re-runs the block with the serial decoder
+// (inflate_serial.cuh), which owns the exact error semantics of the reference.
 //
 // CTAs are persistent: each takes streams from an atomic ticket (the host orders streams longest
 // first), so per-CTA scratch in HBM is bounded by the number of resident CTAs.
 //
 // Replaces the reference's serial token loop Stream.readBlock(with:) and InflatorOut.expand
-// (Sources/LZ77/Inflator/LZ77.InflatorBuffers.Stream.swift:266-381, LZ77.InflatorOut.swift:124-140)
-// and, for zlib streams, the running MRC32 (Sources/LZ77/Wrappers/LZ77.MRC32.swift:26-47).
+// (Sources/LZ77/Inflator/LZ77.InflatorBuffers.Stream.swift:266-381, LZ77.InflatorOut.swift:124-140),
+// the window of LZ77.InflatorOut (LZ77.InflatorOut.swift:86-110) and, for zlib streams, the running
+// MRC32 (Sources/LZ77/Wrappers/LZ77.MRC32.swift:26-47).
 #pragma once
 
 #include "inflate_serial.cuh"
 
 namespace pngb200 {
 
-#ifndef WV_TCAP
-#define WV_TCAP 64
-#endif
 #ifndef WV_CTAS
 #define WV_CTAS 2
 #endif
@@ -66,8 +68,9 @@ constexpr uint32_t WV_SUB_BITS     = 256;
 constexpr uint32_t WV_BITS         = WV_THREADS * WV_SUB_BITS;          // 65536 bits per wave
 constexpr uint32_t WV_WORDS        = WV_BITS / 32 + 8;                  // + look-ahead for the last token
 constexpr uint32_t WV_SMEM_WORDS   = WV_WORDS + WV_WORDS / 8 + 1;
-constexpr uint32_t WV_TOKENS       = WV_TCAP;                           // staged tokens per thread
-constexpr uint32_t WV_OUT_BYTES    = 16384;                             // wave output image in smem
+constexpr uint32_t WV_RING         = 65536;                             // window + wave output (uint16 index wraps)
+constexpr uint32_t WV_WINDOW       = 32768;                             // DEFLATE's largest distance
+constexpr uint32_t WV_OUT_BYTES    = WV_RING - WV_WINDOW;               // largest wave the ring can take
 constexpr uint32_t WV_BITMAP_WORDS = WV_OUT_BYTES / 32;
 constexpr uint32_t WV_LIST_CAP     = WV_BITS / 2 + 64;                  // >= copies per wave (2 bits min each)
 constexpr uint64_t WV_MAX_WAVE_OUT = (uint64_t)WV_LIST_CAP * 258;
@@ -87,7 +90,6 @@ inline void wv_count(int phase, uint32_t iters)
     if ((threadIdx.x & 31) == 0) wv_profile().warp_iters[phase] += m;
 }
 #define WV_COUNT(phase, iters) wv_count(phase, iters)
-inline std::vector<uint16_t>& wv_walks() { static std::vector<uint16_t> v; return v; }
 #else
 #define WV_COUNT(phase, iters)
 #endif
@@ -105,22 +107,19 @@ struct WvHeader {  // block header as parsed by warp 0, broadcast to the CTA
 struct WvShared {
     SerialShared ser;
     uint32_t     words[WV_SMEM_WORDS];
-    uint32_t     tok[WV_TOKENS * WV_THREADS];   // [k][t]: token k of thread t
+    uint32_t     mask[8 * WV_THREADS];          // [k][t]: token starts in bits 32k .. 32k+31 of subsequence t
+    uint16_t     ckn[8 * WV_THREADS];           // [k][t]: bytes produced by thread t's tokens that start before bit 32k
+    uint8_t      ckc[8 * WV_THREADS];           //         copies among them
     uint32_t     exit_[WV_THREADS];             // where thread t's own decode left its subsequence
     uint32_t     wpos_[WV_THREADS];             // where thread t's walk is / ended (wave-relative bit)
     uint32_t     wn_[WV_THREADS];               // bytes produced by the walk
-    uint32_t     ovf_[WV_THREADS];              // bit position of list entry #WV_TOKENS (first one not staged)
-    uint16_t     ntok_[WV_THREADS];             // own tokens of thread t (list entries [0, ntok))
-    uint16_t     wtok_[WV_THREADS];             // walk tokens (list entries [ntok, ntok + wtok))
     uint16_t     wc_[WV_THREADS];               // copies among the walk's tokens
+    uint16_t     next_[WV_THREADS];             // subsequence the walk joined, 0xffff: the chain ends with thread t
     uint8_t      kind_[WV_THREADS];             // WK_*
     uint8_t      wlist[2][WV_THREADS];          // unfinished walks of a round, compacted
     uint32_t     wcount[3];
     uint32_t     bitmap[WV_BITMAP_WORDS];
-    union {                                     // the visited maps die before the image is written
-        uint8_t  outbuf[WV_OUT_BYTES + 32];
-        uint32_t mask[8 * WV_THREADS];          // [k][t]: bits 32k .. 32k+31 of subsequence t
-    } u __align__(16);
+    uint8_t      ring[WV_RING] __align__(16);
     uint64_t     warp_sums[WV_WARPS + 1];
     uint32_t     adler_a[WV_WARPS], adler_b[WV_WARPS];
     uint32_t     exc[WV_WARPS], valid[WV_WARPS];
@@ -211,17 +210,14 @@ __device__ __forceinline__ uint32_t fast_lookup(saddr_t table_addr, uint32_t bit
     return e;
 }
 
-// token word: literal = the byte; copy = 1 << 31 | (distance - 1) << 9 | run
-__device__ __forceinline__ uint32_t tok_is_copy(uint32_t tok) { return tok >> 31; }
-__device__ __forceinline__ uint32_t tok_run(uint32_t tok) { return tok & 511u; }
-__device__ __forceinline__ uint32_t tok_dist(uint32_t tok) { return ((tok >> 9) & 0x7fffu) + 1u; }
-__device__ __forceinline__ uint32_t tok_bytes(uint32_t tok) { return tok_is_copy(tok) ? tok_run(tok) : 1u; }
-
 // Decode one token at the reader's position.  Literal and copy tokens run through ONE predicated
 // body: in a warp some lanes always hold a literal while others hold a copy, so two divergent paths
 // would cost their sum every iteration.  Returns 0, PF_EOB (consumed) or PF_BAD (reader not advanced
-// past the offending code).
-__device__ __forceinline__ uint32_t wv_decode(FastBits& b, saddr_t lit, saddr_t dst, uint32_t& tok)
+// past the offending code).  `run`: bytes the token produces; `dist`: 0 for a literal (then `lit_byte`
+// is the byte), else the LZ77 distance (only computed when WANT_DIST).
+template <bool WANT_DIST>
+__device__ __forceinline__ uint32_t wv_decode(FastBits& b, saddr_t lit, saddr_t dst, uint32_t& run, uint32_t& dist,
+                                              uint32_t& is_copy)
 {
     const uint32_t bits = b.peek();
     const uint32_t e = fast_lookup<LIT_ROOT>(lit, bits);
@@ -231,16 +227,15 @@ __device__ __forceinline__ uint32_t wv_decode(FastBits& b, saddr_t lit, saddr_t 
         return PF_EOB;
     }
     const uint32_t len = e & 15u, skipn = (e >> 4) & 31u;
-    const uint32_t run = (e >> 16) + bfe32(bits, len, skipn - len);  // literals: width 0
+    run = (e >> 16) + bfe32(bits, len, skipn - len);  // literals: width 0, value = the byte
     b.skip(skipn);
-    const uint32_t copy = e & E_COPY;
+    is_copy = (e >> 9) & 1u;
     const uint32_t dbits = b.peek();
     const uint32_t d = fast_lookup<DIST_ROOT>(dst, dbits);  // ignored for literals
-    if (copy && (d & E_SPECIAL)) return PF_BAD;
+    if (is_copy && (d & E_SPECIAL)) return PF_BAD;
     const uint32_t dlen = d & 15u, dskip = (d >> 4) & 31u;
-    const uint32_t dist = (d >> 16) + bfe32(dbits, dlen, dskip - dlen);
-    b.skip(copy ? dskip : 0u);
-    tok = copy ? (0x80000000u | (dist - 1u) << 9 | run) : run;
+    if (WANT_DIST) dist = (d >> 16) + bfe32(dbits, dlen, dskip - dlen);
+    b.skip(is_copy ? dskip : 0u);
     return 0;
 }
 
@@ -314,78 +309,82 @@ __device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t a, ui
     return any == 0;
 }
 
-// One LZ77 copy whose needed source bytes are final.  The wave's output lives at `img` (shared
-// memory image, or the HBM destination itself); sources at negative wave offsets are read from
-// HBM at `hbm` (= destination address of wave offset 0).
-__device__ __forceinline__ void lz_copy(uint8_t* img, const uint8_t* hbm, bool img_is_hbm, uint32_t o,
-                                        uint32_t run, uint32_t dist)
+// One LZ77 copy inside the ring (d, s: ring positions of destination and source, taken mod 65536 per
+// byte; the source is final or is produced by this very loop when the ranges overlap).
+__device__ __forceinline__ void ring_copy(uint8_t* ring, uint32_t d, uint32_t s, uint32_t run, uint32_t dist)
 {
-    const int64_t src = (int64_t)o - (int64_t)dist;
-    uint8_t*      to  = img + o;
-    if (run <= 4 && dist >= 4 && (img_is_hbm || src >= 0 || src + (int64_t)run <= 0)) {
-        // the common short copy: all loads first, then the stores
-        const uint8_t* from = (img_is_hbm || src < 0) ? hbm + src : img + src;
-        uint8_t b0 = from[0], b1 = from[1], b2 = from[2], b3 = run == 4 ? from[3] : 0;
-        to[0] = b0; to[1] = b1; to[2] = b2;
-        if (run == 4) to[3] = b3;
-        return;
-    }
-    if (img_is_hbm || src >= 0 || src + (int64_t)run <= 0) {
-        const uint8_t* from = (img_is_hbm || src < 0) ? hbm + src : img + src;
-        if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
-            uint32_t k = 0;
-            for (; k + 4 <= run; k += 4) {
-                uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
-                to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3;
-            }
-            for (; k < run; ++k) to[k] = from[k];
-        } else {
-            uint32_t q = 0;
-            for (uint32_t k = 0; k < run; ++k) {
-                to[k] = from[q];
-                if (++q == dist) q = 0;
-            }
+    if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
+        uint32_t k = 0;
+        for (; k + 4 <= run; k += 4) {
+            const uint8_t b0 = ring[(s + k) & 0xffffu], b1 = ring[(s + k + 1) & 0xffffu],
+                          b2 = ring[(s + k + 2) & 0xffffu], b3 = ring[(s + k + 3) & 0xffffu];
+            ring[(d + k) & 0xffffu] = b0;
+            ring[(d + k + 1) & 0xffffu] = b1;
+            ring[(d + k + 2) & 0xffffu] = b2;
+            ring[(d + k + 3) & 0xffffu] = b3;
         }
+        for (; k < run; ++k) ring[(d + k) & 0xffffu] = ring[(s + k) & 0xffffu];
     } else {
-        // source starts behind the wave (HBM) and runs into the image: byte k comes from wave
-        // offset src + k; offsets < 0 are in HBM, the rest were written earlier by this loop
+        for (uint32_t k = 0; k < run; ++k) ring[(d + k) & 0xffffu] = ring[(s + k) & 0xffffu];
+    }
+}
+
+// The same for an oversized wave, whose output and sources live in HBM (`hbm` = address of wave
+// offset 0; the source is final or produced by this very loop).
+__device__ __forceinline__ void hbm_copy(uint8_t* hbm, uint32_t o, uint32_t run, uint32_t dist)
+{
+    uint8_t*       to   = hbm + o;
+    const uint8_t* from = to - dist;
+    if (dist >= 4) {
+        uint32_t k = 0;
+        for (; k + 4 <= run; k += 4) {
+            const uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
+            to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3;
+        }
+        for (; k < run; ++k) to[k] = from[k];
+    } else {
+        uint32_t q = 0;
         for (uint32_t k = 0; k < run; ++k) {
-            const int64_t p = src + (int64_t)k;
-            to[k] = p < 0 ? hbm[p] : img[p];
+            to[k] = from[q];
+            if (++q == dist) q = 0;
         }
     }
 }
 
 // per-thread emit state: where the next byte goes, which of the thread's own bytes are final
 struct EmitState {
-    uint8_t*       img;       // wave output image (shared memory, or HBM for oversized waves)
-    const uint8_t* hbm;       // HBM address of wave offset 0
-    uint32_t*      U;         // unresolved bitmap
-    CopyItem*      list;
-    uint64_t       out;       // stream offset of wave offset 0
-    uint32_t       o;         // next output byte (wave-relative)
-    uint32_t       clean;     // my bytes in [clean, o) are final
-    uint32_t       c_next;    // my next list slot
-    uint32_t       mw, mbits; // pending unresolved-bit word
-    bool           in_hbm;
-    bool           bad_ref;   // invalidStringReference seen
+    uint8_t*  ring;      // shared-memory ring
+    uint32_t  rbase;     // ring position of wave offset 0
+    uint8_t*  hbm;       // HBM address of wave offset 0 (oversized waves write here directly)
+    uint32_t* U;         // unresolved bitmap
+    CopyItem* list;
+    uint64_t  out;       // stream offset of wave offset 0
+    uint32_t  o;         // next output byte (wave-relative)
+    uint32_t  clean;     // my bytes in [clean, o) are final
+    uint32_t  c_next;    // my next list slot
+    uint32_t  mw, mbits; // pending unresolved-bit word
+    bool      bad_ref;   // invalidStringReference seen
 };
 
-__device__ __forceinline__ void emit_token(EmitState& S, uint32_t tok)
+template <bool IN_HBM>
+__device__ __forceinline__ void emit_token(EmitState& S, uint32_t run, uint32_t dist, uint32_t is_copy)
 {
-    if (!tok_is_copy(tok)) {
-        S.img[S.o++] = (uint8_t)tok;
+    if (!is_copy) {
+        if (IN_HBM) S.hbm[S.o] = (uint8_t)run;
+        else S.ring[(S.rbase + S.o) & 0xffffu] = (uint8_t)run;
+        ++S.o;
         return;
     }
-    const uint32_t run = tok_run(tok), dist = tok_dist(tok), o = S.o;
+    const uint32_t o = S.o;
     if ((uint64_t)dist > S.out + o) {  // invalidStringReference: the serial decoder reports it
         S.bad_ref = true;
         return;
     }
-    const int64_t src = (int64_t)o - (int64_t)dist;
-    if (src + (int64_t)run <= 0 || src >= (int64_t)S.clean) {
-        // source is final: behind the wave (HBM), or inside this thread's own finished bytes
-        lz_copy(S.img, S.hbm, S.in_hbm, o, run, dist);
+    const int32_t src = (int32_t)o - (int32_t)dist;
+    if (src + (int32_t)run <= 0 || src >= (int32_t)S.clean) {
+        // source is final: behind the wave (the window), or inside this thread's own finished bytes
+        if (IN_HBM) hbm_copy(S.hbm, o, run, dist);
+        else ring_copy(S.ring, S.rbase + o, S.rbase + o - dist, run, dist);
     } else {
         // flag [o, o + run) as unresolved; words are flushed once, when left
         for (uint32_t a = o, e2 = o + run; a < e2;) {
@@ -436,6 +435,7 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
     for (uint32_t k = t; k < WV_BITMAP_WORDS; k += WV_THREADS) sh.bitmap[k] = 0;
     const saddr_t words_addr = smem_addr(sh.words);
     const saddr_t lit = smem_addr(sh.ser.lit), dstt = smem_addr(sh.ser.dist);
+    uint32_t* const mk = sh.mask;
 
     for (;;) {
         __syncthreads();
@@ -454,13 +454,15 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
         BitReader br;
         br.init(job.src, job.src_len, job.start_bit);
         uint64_t out    = job.start_out;
-        uint32_t blocks = 0, waves = 0, walk_tokens = 0, resolve_rounds = 0;
-        uint64_t n_tokens = 0, n_matches = 0, n_deferred = 0;
+        uint32_t blocks = 0, waves = 0, resolve_rounds = 0;
+        uint64_t n_tokens = 0, n_matches = 0, n_deferred = 0, walk_tokens = 0;
         int      st     = PNGB200_OK;
         uint32_t phase  = (uint32_t)job.phase;
         uint64_t resume_bit = job.start_bit, resume_out = job.start_out;
         uint8_t* const dst = job.dst;
+        const uint32_t mis = (uint32_t)((uintptr_t)dst & 15);  // ring position = stream offset + mis (mod 65536)
         bool fallback = false;
+        bool ring_stale = job.start_out != 0;   // the ring does not hold the window [out - 32768, out)
         // running Adler-32 (thread 0): valid when this launch sees the stream from its first byte
         const bool adler_on = job.start_out == 0;
         uint32_t   s1 = 1, s2 = 0;
@@ -492,7 +494,6 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
             pend = true;
             pend_len = n;
         };
-
         // phase timer: thread 0 charges the cycles since the last tick to phase `i`
         auto tick = [&](int i) {
             if (t == 0) {
@@ -546,6 +547,7 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                 const uint8_t* s = job.src + (br.at() >> 3);
                 for (uint32_t k = t; k < stored; k += WV_THREADS) dst[out + k] = s[k];
                 if (adler_on && stored) adler_hbm(s, stored);
+                if (stored) ring_stale = true;
                 out += stored;
                 br.seek(br.pos + 8 * (uint64_t)stored);
                 __syncthreads();
@@ -561,46 +563,48 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     __syncthreads();
                     for (uint32_t k = t; k < WV_WORDS; k += WV_THREADS)
                         sh.words[k + (k >> 3)] = br.load_word(wbase + k);
+                    if (t == 0) sh.wcount[0] = 0;
                     __syncthreads();                                      // (1)
                     fold_adler();
                     tick(1);
                     const uint32_t rel0  = (uint32_t)(wstart - (wbase << 5));  // < 256
                     const uint32_t base  = t * WV_SUB_BITS;
                     const uint32_t limit = base + WV_SUB_BITS;
-                    uint32_t* const mk = sh.u.mask;
 
-                    // ---- A. speculative decode of my subsequence ----
-                    uint32_t n = 0, nout = 0, ncopy = 0, flags = 0, exit_bit;
+                    // ---- A. speculative decode of my subsequence: token-start map, checkpoints, totals ----
+                    uint32_t nout = 0, ncopy = 0, flags = 0, exit_bit;
                     {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) mk[k * WV_THREADS + t] = 0;
+                        sh.ckn[t] = 0;
+                        sh.ckc[t] = 0;
                         FastBits b;
                         b.init(words_addr, t == 0 ? rel0 : base);
-                        uint32_t mi = 0, mw = 0;
+                        uint32_t mi = 0, mw = 0, n = 0;
                         while (b.pos < limit) {
                             const uint32_t rr = b.pos - base, wi = rr >> 5;
                             if (wi != mi) {
                                 mk[mi * WV_THREADS + t] = mw;
                                 mw = 0;
-                                mi = wi;
+                                do {   // counts of the tokens that start before bit 32 * mi
+                                    ++mi;
+                                    sh.ckn[mi * WV_THREADS + t] = (uint16_t)nout;
+                                    sh.ckc[mi * WV_THREADS + t] = (uint8_t)ncopy;
+                                } while (mi != wi);
                             }
                             mw |= 1u << (rr & 31);
-                            uint32_t tok = 0;
-                            const uint32_t s = wv_decode(b, lit, dstt, tok);
+                            uint32_t run = 0, dist = 0, cp = 0;
+                            const uint32_t s = wv_decode<false>(b, lit, dstt, run, dist, cp);
                             if (s) { flags = s; break; }
-                            if (n < WV_TOKENS) sh.tok[n * WV_THREADS + t] = tok;
-                            else if (n == WV_TOKENS) sh.ovf_[t] = base + rr;   // where list entry #WV_TOKENS starts
+                            nout += cp ? run : 1u;
+                            ncopy += cp;
                             ++n;
-                            nout += tok_bytes(tok);
-                            ncopy += tok_is_copy(tok);
                         }
                         mk[mi * WV_THREADS + t] = mw;
                         exit_bit = b.pos;
+                        WV_COUNT(0, n);
                     }
-                    sh.ntok_[t] = (uint16_t)n;
                     sh.exit_[t] = exit_bit;
-                    if (t == 0) sh.wcount[0] = 0;
-                    WV_COUNT(0, n);
                     __syncthreads();                                      // (2) maps complete
                     tick(2);
 
@@ -609,21 +613,19 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     //      8, 16, 32 ... tokens; the unfinished walks of a round are compacted onto the lowest
                     //      threads (state in shared memory), so that a round costs what it still has to do ----
                     {
-                        uint32_t u = t, pos = exit_bit, wn = 0, wc = 0, wtok = 0;
+                        uint32_t u = t, pos = exit_bit, wn = 0, wc = 0;
                         bool     active = flags == 0;
                         if (!active) {
                             sh.kind_[t] = (uint8_t)(flags == PF_EOB ? WK_OWN_EOB : WK_OWN_BAD);
                             sh.wpos_[t] = exit_bit;
                             sh.wn_[t] = 0;
                             sh.wc_[t] = 0;
-                            sh.wtok_[t] = 0;
                         }
                         for (uint32_t round = 0;; ++round) {
                             const uint32_t K = WV_WALK_K << min(round, 6u);
                             bool     still = false;
                             uint32_t iters = 0;
                             if (active) {
-                                const uint32_t nu = sh.ntok_[u];
                                 FastBits b;
                                 b.init(words_addr, pos);
                                 uint32_t kind = WK_RUNNING;
@@ -632,23 +634,18 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                                     if (p >= WV_BITS) { kind = WK_END; break; }
                                     const uint32_t s = p >> 8, rr = p & 255u;
                                     if ((mk[(rr >> 5) * WV_THREADS + s] >> (rr & 31)) & 1u) { kind = WK_SYNC; break; }
-                                    uint32_t tok = 0;
-                                    const uint32_t e = wv_decode(b, lit, dstt, tok);
+                                    uint32_t run = 0, dist = 0, cp = 0;
+                                    const uint32_t e = wv_decode<false>(b, lit, dstt, run, dist, cp);
                                     if (e) { kind = e == PF_EOB ? WK_EOB : WK_BAD; break; }
-                                    // the walk's tokens continue the list of the thread it started from
-                                    const uint32_t slot = nu + wtok;
-                                    if (slot < WV_TOKENS) sh.tok[slot * WV_THREADS + u] = tok;
-                                    else if (slot == WV_TOKENS) sh.ovf_[u] = p;
-                                    wn += tok_bytes(tok);
-                                    wc += tok_is_copy(tok);
-                                    ++wtok;
+                                    wn += cp ? run : 1u;
+                                    wc += cp;
                                 }
                                 sh.wpos_[u] = b.pos;
                                 sh.wn_[u]   = wn;
                                 sh.wc_[u]   = (uint16_t)wc;
-                                sh.wtok_[u] = (uint16_t)wtok;
                                 sh.kind_[u] = (uint8_t)kind;
                                 still = kind == WK_RUNNING;
+                                walk_tokens += iters;
                             }
                             WV_COUNT(1, iters);
                             if (t == 0) sh.wcount[(round + 1) % 3] = 0;
@@ -665,96 +662,88 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                             if (cnt == 0) break;
                             active = t < cnt;
                             if (active) {
-                                u    = sh.wlist[round & 1][t];
-                                pos  = sh.wpos_[u];
-                                wn   = sh.wn_[u];
-                                wc   = sh.wc_[u];
-                                wtok = sh.wtok_[u];
+                                u   = sh.wlist[round & 1][t];
+                                pos = sh.wpos_[u];
+                                wn  = sh.wn_[u];
+                                wc  = sh.wc_[u];
                             }
                         }
                     }
                     tick(3);
                     const uint32_t kind = sh.kind_[t], wpos = sh.wpos_[t];
-#if defined(PNGB200_EMU) && defined(WV_PROFILE)
-                    wv_walks().push_back((uint16_t)sh.wtok_[t]);
-                    wv_walks().push_back((uint16_t)n);
-                    wv_walks().push_back((uint16_t)t);
-#endif
                     {
-                        const unsigned e = __ballot_sync(0xffffffffu, !(kind == WK_SYNC && (wpos >> 8) == t + 1));
+                        const bool joins_next = kind == WK_SYNC && (wpos >> 8) == t + 1;
+                        sh.next_[t] = (uint16_t)(kind == WK_SYNC ? wpos >> 8 : 0xffffu);
+                        const unsigned e = __ballot_sync(0xffffffffu, !joins_next);
                         if (lane == 0) sh.exc[warp] = e;
                     }
                     __syncthreads();                                      // (3)
 
-                    // ---- C. the true chain: orbit of thread 0 (one thread, steps only at exceptions) ----
+                    // ---- C. the true chain: orbit of thread 0.  One thread, exception words in registers, one
+                    //      shared-memory load per walk that did not simply join the next subsequence ----
                     if (t == 0) {
-                        uint32_t V[WV_WARPS];
+                        uint32_t E[WV_WARPS];
 #pragma unroll
-                        for (int w = 0; w < WV_WARPS; ++w) V[w] = 0;
+                        for (int w = 0; w < WV_WARPS; ++w) E[w] = sh.exc[w];
                         uint32_t cur = 0, x = 0;
-                        for (;;) {
-                            uint32_t w = cur >> 5, m = sh.exc[w] & (~0u << (cur & 31));
-                            while (m == 0) m = sh.exc[++w];   // thread 255 never joins anybody: always found
-                            x = w * 32 + (uint32_t)__ffs((int)m) - 1;
-                            // threads cur .. x are on the chain
-                            for (uint32_t a = cur; a <= x;) {
-                                const uint32_t vw = a >> 5, hi = min(x + 1, (vw + 1) << 5);
+                        bool     done = false;
 #pragma unroll
-                                for (int q = 0; q < WV_WARPS; ++q)
-                                    if (q == (int)vw) V[q] |= bit_mask(a & 31, ((hi - 1) & 31) + 1);
-                                a = hi;
+                        for (int w = 0; w < WV_WARPS; ++w) {
+                            uint32_t v = 0;
+                            while (!done && cur < 32u * (w + 1)) {   // cur >= 32 w here
+                                const uint32_t lo = cur - 32u * w;
+                                const uint32_t m = E[w] & (~0u << lo);
+                                if (m == 0) {                        // the rest of this word joins its neighbour
+                                    v |= ~0u << lo;
+                                    cur = 32u * (w + 1);
+                                    break;
+                                }
+                                const uint32_t b = (uint32_t)__ffs((int)m) - 1;
+                                x = 32u * w + b;
+                                v |= bit_mask(lo, b + 1);            // threads cur .. x are on the chain
+                                const uint32_t nx = sh.next_[x];
+                                if (nx == 0xffffu) done = true;      // thread 255 never joins anybody: always reached
+                                else cur = nx;                       // > x + 1: the walk crossed subsequences
                             }
-                            if (sh.kind_[x] != WK_SYNC) break;
-                            cur = sh.wpos_[x] >> 8;   // > x + 1: the walk crossed subsequences without joining
+                            sh.valid[w] = v;
                         }
-#pragma unroll
-                        for (int w = 0; w < WV_WARPS; ++w) sh.valid[w] = V[w];
                         sh.last = x;
                         sh.term = sh.kind_[x];
                     }
                     __syncthreads();                                      // (4)
                     tick(4);
 
-                    // ---- D. my share of the chain: the tokens that START in my subsequence = the walk of my
-                    //      predecessor on the chain (up to the position where it joined me) + my own tokens from
-                    //      there on; the last thread of the chain adds its own walk ----
+                    // ---- D. my share of the chain: the tokens that START in my subsequence, i.e. from the exit
+                    //      of my predecessor on the chain to my own exit (the last thread adds its own walk) ----
                     const bool     on_chain = (sh.valid[warp] >> lane) & 1u;
-#if defined(PNGB200_EMU) && defined(WV_PROFILE)
-                    wv_walks()[wv_walks().size() - 3 * (WV_THREADS - t) + 2] = (uint16_t)on_chain;
-#endif
                     const uint32_t last = sh.last, term = sh.term;
-                    uint32_t k0 = 0, p0 = rel0;      // index / position of my first valid token
-                    uint32_t pred = 0, pw = 0;       // predecessor on the chain, tokens of its walk
+                    uint32_t from = rel0;            // where my share starts
                     uint32_t my_nout = 0, my_ncopy = 0;
                     if (on_chain) {
-                        uint32_t pn = 0, pc = 0;
+                        uint32_t pn = 0, pc = 0, pre_n = 0, pre_c = 0;
                         if (t > 0) {
                             uint32_t w = warp, m = sh.valid[w] & ((1u << lane) - 1u);
                             while (m == 0) m = sh.valid[--w];
-                            pred = w * 32 + 31 - (uint32_t)__clz((int)m);
-                            p0 = sh.wpos_[pred];
-                            pw = sh.wtok_[pred];
+                            const uint32_t pred = w * 32 + 31 - (uint32_t)__clz((int)m);
+                            const uint32_t p0 = sh.wpos_[pred];       // where the predecessor's walk joined me
+                            from = sh.exit_[pred];
                             pn = sh.wn_[pred];
                             pc = sh.wc_[pred];
-                            const uint32_t rr = p0 - base, full = rr >> 5;
-                            for (uint32_t q = 0; q < full; ++q) k0 += (uint32_t)__popc(mk[q * WV_THREADS + t]);
-                            k0 += (uint32_t)__popc(mk[full * WV_THREADS + t] & ((1u << (rr & 31)) - 1u));
-                        }
-                        uint32_t pre_n = 0, pre_c = 0;
-                        const uint32_t kk = min(k0, min(n, WV_TOKENS));
-                        for (uint32_t i = 0; i < kk; ++i) {
-                            const uint32_t tok = sh.tok[i * WV_THREADS + t];
-                            pre_n += tok_bytes(tok);
-                            pre_c += tok_is_copy(tok);
-                        }
-                        if (k0 > WV_TOKENS) {  // joined behind the staged tokens: count the rest of the prefix
-                            FastBits b;
-                            b.init(words_addr, sh.ovf_[t]);
-                            while (b.pos != p0 && b.pos < limit) {
-                                uint32_t tok = 0;
-                                if (wv_decode(b, lit, dstt, tok)) break;
-                                pre_n += tok_bytes(tok);
-                                pre_c += tok_is_copy(tok);
+                            // my garbage prefix: tokens of mine that start before p0 = checkpoint of p0's map
+                            // word + the tokens between the first start in that word and p0
+                            const uint32_t rr = p0 - base, q = rr >> 5;
+                            pre_n = sh.ckn[q * WV_THREADS + t];
+                            pre_c = sh.ckc[q * WV_THREADS + t];
+                            const uint32_t first = (uint32_t)__ffs((int)mk[q * WV_THREADS + t]) - 1;
+                            if (first != (rr & 31)) {
+                                FastBits b;
+                                b.init(words_addr, base + 32 * q + first);
+                                while (b.pos != p0 && b.pos < limit) {
+                                    uint32_t run = 0, dist = 0, cp = 0;
+                                    if (wv_decode<false>(b, lit, dstt, run, dist, cp)) break;
+                                    pre_n += cp ? run : 1u;
+                                    pre_c += cp;
+                                }
                             }
                         }
                         my_nout  = pn + nout - pre_n;
@@ -785,64 +774,60 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                         if (lane < WV_WARPS) sh.warp_sums[lane] = wi - ws;  // exclusive
                         if (lane == WV_WARPS - 1) sh.warp_sums[WV_WARPS] = wi;  // wave totals
                     }
-                    __syncthreads();                                      // (6) maps are dead from here
+                    __syncthreads();                                      // (6)
                     tick(5);
                     const uint64_t excl    = sh.warp_sums[warp] + incl - mine;
                     const uint32_t o_start = (uint32_t)(excl & 0xffffffffffull);
                     const uint32_t c_start = (uint32_t)(excl >> 40);           // my first list slot
-                    const uint32_t total   = (uint32_t)(sh.warp_sums[WV_WARPS] & 0xffffffffffull);
+                    const uint64_t total64 = sh.warp_sums[WV_WARPS] & 0xffffffffffull;
                     const uint32_t np      = (uint32_t)(sh.warp_sums[WV_WARPS] >> 40);
-                    if (sh.anomaly || out + total > job.dst_cap || total > P.bitmap_words * 32) {
+                    if (sh.anomaly || out + total64 > job.dst_cap || total64 > P.bitmap_words * 32) {
                         fallback = true;
                         break;
                     }
-                    // ---- E. emit: replay my staged tokens, decode my walk segment ----
+                    const uint32_t  total  = (uint32_t)total64;
+                    // ---- E. emit: decode my share once more and write it ----
                     uint8_t* const  wdst   = dst + out;           // HBM address of wave offset 0
-                    const uint32_t  shift  = (uint32_t)((uintptr_t)wdst & 15);
                     const bool      in_hbm = total > WV_OUT_BYTES;
-                    uint8_t* const  img    = in_hbm ? wdst : sh.u.outbuf + shift;
+                    const uint32_t  rbase  = (uint32_t)(out + mis) & 0xffffu;  // ring position of wave offset 0
                     uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
-                    uint32_t deferred = 0;
-                    uint32_t replayed = 0, redone = 0;
+                    if (!in_hbm && ring_stale) {
+                        // the window [out - 32768, out) was written to HBM behind the ring's back: fetch it
+                        const uint64_t lo = out > WV_WINDOW ? out - WV_WINDOW : 0;
+                        for (uint64_t x = lo + t; x < out; x += WV_THREADS) sh.ring[(x + mis) & 0xffffu] = dst[x];
+                        __syncthreads();
+                    }
+                    ring_stale = in_hbm;
+                    uint32_t deferred = 0, emitted = 0;
                     if (on_chain) {
                         EmitState S;
-                        S.img = img; S.hbm = wdst; S.U = U; S.list = list; S.out = out;
+                        S.ring = sh.ring; S.rbase = rbase; S.hbm = wdst; S.U = U; S.list = list; S.out = out;
                         S.o = o_start; S.clean = o_start; S.c_next = c_start;
-                        S.mw = o_start >> 5; S.mbits = 0; S.in_hbm = in_hbm; S.bad_ref = false;
-                        // entries [a, b) of thread u's token list, covering the bits [from, to) of the wave
-                        auto emit_segment = [&](uint32_t u, uint32_t a, uint32_t b, uint32_t from, uint32_t to) {
-                            const uint32_t kend = min(b, WV_TOKENS);
-                            for (uint32_t k = a; k < kend; ++k) emit_token(S, sh.tok[k * WV_THREADS + u]);
-                            replayed += kend > a ? kend - a : 0;
-                            if (b > WV_TOKENS) {
-                                // what did not fit the staging area is decoded again (rare: > WV_TOKENS tokens
-                                // in 256 bits + walk)
-                                FastBits bb;
-                                bb.init(words_addr, a > WV_TOKENS ? from : sh.ovf_[u]);
-                                while (bb.pos != to && bb.pos < WV_BITS + 64) {
-                                    uint32_t tok = 0;
-                                    if (wv_decode(bb, lit, dstt, tok)) break;
-                                    emit_token(S, tok);
-                                    ++redone;
-                                }
+                        S.mw = o_start >> 5; S.mbits = 0; S.bad_ref = false;
+                        const uint32_t to = t == last ? wpos : exit_bit;
+                        FastBits b;
+                        b.init(words_addr, from);
+                        if (in_hbm) {
+                            while (b.pos != to && b.pos < WV_BITS + 64) {
+                                uint32_t run = 0, dist = 0, cp = 0;
+                                if (wv_decode<true>(b, lit, dstt, run, dist, cp)) break;
+                                emit_token<true>(S, run, dist, cp);
+                                ++emitted;
                             }
-                        };
-                        if (pw) {
-                            const uint32_t a = sh.ntok_[pred];
-                            emit_segment(pred, a, a + pw, sh.exit_[pred], p0);
+                        } else {
+                            while (b.pos != to && b.pos < WV_BITS + 64) {
+                                uint32_t run = 0, dist = 0, cp = 0;
+                                if (wv_decode<true>(b, lit, dstt, run, dist, cp)) break;
+                                emit_token<false>(S, run, dist, cp);
+                                ++emitted;
+                            }
                         }
-                        emit_segment(t, k0, n, p0, exit_bit);
-                        if (t == last && sh.wtok_[t]) emit_segment(t, n, n + sh.wtok_[t], exit_bit, wpos);
                         if (S.mbits) atomicOr(U + S.mw, S.mbits);
                         if (S.bad_ref) sh.anomaly = 1;
                         deferred = S.c_next - c_start;
                         for (uint32_t c = S.c_next; c < c_start + my_ncopy; ++c) list[c] = CopyItem{0, 0};
                     }
-#if defined(PNGB200_EMU) && defined(WV_PROFILE)
-                    wv_walks()[wv_walks().size() - 3 * (WV_THREADS - t) + 1] = (uint16_t)replayed;
-#endif
-                    WV_COUNT(2, replayed);
-                    WV_COUNT(3, redone);
+                    WV_COUNT(2, emitted);
                     __threadfence_block();
                     __syncthreads();                                      // (7)
                     tick(6);
@@ -878,18 +863,19 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                                 bool ready = true;
                                 if (hi > 0) ready = bits_all_clear(U, (uint32_t)max(src, (int64_t)0), (uint32_t)hi);
                                 if (ready) {
-                                    lz_copy(img, wdst, in_hbm, it.o, run, dist);
+                                    if (in_hbm) hbm_copy(wdst, it.o, run, dist);
+                                    else ring_copy(sh.ring, rbase + it.o, rbase + it.o - dist, run, dist);
                                     __threadfence_block();
                                     bits_clear(U, it.o, it.o + run);
                                     have = false;
                                     progressed = true;
                                 }
                             }
-                            ++resolve_rounds;
                             ++rounds;
                             if (!__any_sync(0xffffffffu, have || have_nxt)) break;
                             if (!__any_sync(0xffffffffu, progressed)) __nanosleep(40);
                         }
+                        resolve_rounds += rounds;
                         WV_COUNT(4, rounds);
                     }
                     __threadfence_block();
@@ -901,22 +887,23 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                         fallback = true;
                         break;
                     }
-                    // ---- G. store: shared-memory image -> HBM, 16-byte coalesced; Adler-32 partial sums ----
+                    // ---- G. store: ring -> HBM, 16-byte coalesced; Adler-32 partial sums from the same registers ----
                     if (!in_hbm && total) {
-                        uint8_t* const       gbase = wdst - shift;           // 16-byte aligned
-                        const uint32_t       end   = shift + total;          // bytes [shift, end) are ours
-                        const uint32_t       nq    = (end + 15) >> 4;
-                        const uint4* const   q     = reinterpret_cast<const uint4*>(sh.u.outbuf);
+                        const uint32_t shift = rbase & 15u;                  // == (uintptr_t)wdst & 15
+                        uint8_t* const gbase = wdst - shift;                 // 16-byte aligned
+                        const uint32_t rb16  = rbase - shift;                // ring position of gbase
+                        const uint32_t end   = shift + total;                // bytes [shift, end) are ours
+                        const uint32_t nq    = (end + 15) >> 4;
                         uint64_t a = 0, bw = 0;
                         for (uint32_t c = t; c < nq; c += WV_THREADS) {
                             const uint32_t lo = c << 4, hi = lo + 16;
                             if (lo >= shift && hi <= end) {
-                                const uint4 x = q[c];
+                                const uint4 x = *reinterpret_cast<const uint4*>(sh.ring + ((rb16 + lo) & 0xffffu));
                                 reinterpret_cast<uint4*>(gbase)[c] = x;
                                 adler_chunk16(x, end - lo, a, bw);
                             } else {
                                 for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) {
-                                    const uint8_t v = sh.u.outbuf[k];
+                                    const uint8_t v = sh.ring[(rb16 + k) & 0xffffu];
                                     gbase[k] = v;
                                     a += v;
                                     bw += (uint64_t)(end - k) * v;
@@ -938,9 +925,8 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     }
                     tick(8);
                     out += total;
-                    walk_tokens += sh.wtok_[t];
-                    if (t == 0) { n_matches += np; }
-                    n_tokens += replayed + redone;
+                    if (t == 0) n_matches += np;
+                    n_tokens += emitted;
                     n_deferred += deferred;
                     br.seek((wbase << 5) + sh.wpos_[last]);
                     if (term == WK_EOB || term == WK_OWN_EOB) block_done = true;
@@ -960,8 +946,8 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
         fold_adler();
         // per-stream statistics (the reference's -DDUMP_LZ77_BLOCKS style counters): CTA sums
         {
-            uint64_t v0 = n_tokens, v1 = n_deferred;
-            uint32_t v2 = walk_tokens, v3 = resolve_rounds;
+            uint64_t v0 = n_tokens, v1 = n_deferred, v2 = walk_tokens;
+            uint32_t v3 = resolve_rounds;
             for (int o = 16; o; o >>= 1) {
                 v0 += __shfl_down_sync(0xffffffffu, v0, o);
                 v1 += __shfl_down_sync(0xffffffffu, v1, o);
@@ -971,15 +957,22 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
             if (lane == 0) {
                 sh.warp_sums[warp] = v0;
                 sh.adler_a[warp] = (uint32_t)min(v1, (uint64_t)0xffffffffu);
-                sh.adler_b[warp] = v2;
+                sh.adler_b[warp] = (uint32_t)min(v2, (uint64_t)0xffffffffu);
+                sh.exc[warp] = v3;
             }
             __syncthreads();
             if (t == 0) {
                 uint64_t tk = 0, df = 0, wt = 0;
-                for (int w = 0; w < WV_WARPS; ++w) { tk += sh.warp_sums[w]; df += sh.adler_a[w]; wt += sh.adler_b[w]; }
+                uint32_t rr = 0;
+                for (int w = 0; w < WV_WARPS; ++w) {
+                    tk += sh.warp_sums[w];
+                    df += sh.adler_a[w];
+                    wt += sh.adler_b[w];
+                    rr = max(rr, sh.exc[w]);
+                }
                 r->stat_waves          = waves;
-                r->stat_sync_rounds    = (uint32_t)wt;          // tokens decoded by walks
-                r->stat_resolve_rounds = v3;
+                r->stat_sync_rounds    = (uint32_t)min(wt, (uint64_t)0xffffffffu);   // tokens decoded by walks
+                r->stat_resolve_rounds = rr;
                 r->stat_tokens         = tk;
                 r->stat_matches        = n_matches;
                 r->stat_deferred       = df;

@@ -27,10 +27,3 @@ extern "C" void emu_profile(uint64_t* thread_iters, uint64_t* warp_iters, int re
     for (int i = 0; i < 8; ++i) { thread_iters[i] = wv_profile().thread_iters[i]; warp_iters[i] = wv_profile().warp_iters[i]; }
     if (reset) memset(&wv_profile(), 0, sizeof(WvProfile));
 }
-extern "C" size_t emu_walks(uint16_t* out, size_t cap)
-{
-    size_t n = std::min(cap, wv_walks().size());
-    memcpy(out, wv_walks().data(), 2 * n);
-    wv_walks().clear();
-    return n;
-}
