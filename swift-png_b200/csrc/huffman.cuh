@@ -142,7 +142,10 @@ __device__ void build_table(uint32_t* table, const uint8_t* lens, int nsym, int 
         }
     }
     sync();
-    // fill: one table index per thread-iteration, canonical decode of its MSB-first prefix
+    // roots: one table index per thread-iteration, canonical decode of its MSB-first prefix.  A prefix
+    // shared by longer codes gets a subtable (allocated here, pre-filled with "invalid" for incomplete
+    // codes); the long codes themselves are entered in the next step, one symbol per thread, so that no
+    // thread fills a whole subtable alone
     for (int i = tid; i < (1 << ROOT); i += nt) {
         uint32_t v = __brev((uint32_t)i) >> (32 - ROOT);
         uint32_t e = 0;
@@ -172,23 +175,33 @@ __device__ void build_table(uint32_t* table, const uint8_t* lens, int nsym, int 
                     e = mk_entry(K_INVALID, 0, 0, 0);
                 } else {
                     e = mk_entry(K_PTR, ROOT, (uint32_t)k, slot);
-                    for (uint32_t j = 0; j < (1u << k); ++j) {
-                        uint32_t ext = __brev(j) >> (32 - k);
-                        uint32_t se  = mk_entry(K_INVALID, 0, 0, 0);
-                        for (int l = ROOT + 1; l <= ROOT + k; ++l) {
-                            uint32_t c = (v << (l - ROOT)) | (ext >> (k - (l - ROOT)));
-                            uint32_t d = c - S->first[l];
-                            if (d < S->count[l]) {
-                                se = symbol_entry(alphabet, S->sorted[S->offs[l] + d], (uint32_t)l);
-                                break;
-                            }
-                        }
-                        table[slot + j] = se;
-                    }
+                    const uint32_t inv = mk_entry(K_INVALID, 0, 0, 0);
+                    for (uint32_t j = 0; j < (1u << k); ++j) table[slot + j] = inv;
                 }
             }
         }
         table[i] = e;
+    }
+    sync();
+    // long codes (length > ROOT): the symbol at position idx of sorted[] has the canonical code
+    // first[l] + idx - offs[l]; its subtable index is the reversed tail of the code, replicated over
+    // the subtable's unused high bits
+    if (S->status == 0 && ROOT < 15) {
+        int nlong_from = (int)S->offs[ROOT] + (int)S->count[ROOT];  // first position with length > ROOT
+        int total = (int)S->offs[15] + (int)S->count[15];
+        for (int idx = nlong_from + tid; idx < total; idx += nt) {
+            const uint32_t sym = S->sorted[idx];
+            const uint32_t l   = lens[sym];
+            const uint32_t c   = S->first[l] + (uint32_t)idx - S->offs[l];
+            const uint32_t t2  = l - ROOT;                                    // tail bits
+            const uint32_t v   = c >> t2;                                     // MSB-first root prefix
+            const uint32_t e   = table[__brev(v) >> (32 - ROOT)];
+            if (e_kind(e) != K_PTR) continue;                                 // (allocation failed)
+            const uint32_t k = e_extra(e), slot = e_value(e);
+            const uint32_t jl = __brev(c & ((1u << t2) - 1u)) >> (32 - t2);   // LSB-first tail
+            const uint32_t se = symbol_entry(alphabet, sym, l);
+            for (uint32_t h = 0; h < (1u << (k - t2)); ++h) table[slot + jl + (h << t2)] = se;
+        }
     }
     sync();
 }

@@ -108,15 +108,20 @@ struct WvShared {
     SerialShared ser;
     uint32_t     words[WV_SMEM_WORDS];
     uint32_t     mask[8 * WV_THREADS];          // [k][t]: token starts in bits 32k .. 32k+31 of subsequence t
-    uint16_t     ckn[8 * WV_THREADS];           // [k][t]: bytes produced by thread t's tokens that start before bit 32k
-    uint8_t      ckc[8 * WV_THREADS];           //         copies among them
+    uint32_t     ck[8 * WV_THREADS];            // [k][t]: bytes (low 16 bits) and copies produced by thread t's tokens that
+                                                //         start before map word k (written for words that hold a start)
     uint32_t     exit_[WV_THREADS];             // where thread t's own decode left its subsequence
     uint32_t     wpos_[WV_THREADS];             // where thread t's walk is / ended (wave-relative bit)
     uint32_t     wn_[WV_THREADS];               // bytes produced by the walk
+    uint64_t     cross_[WV_THREADS];            // where the walk first crossed into the subsequence after the one it
+                                                // started in: 1 << 63 | position << 40 | copies << 24 | bytes (0: it did not)
     uint16_t     wc_[WV_THREADS];               // copies among the walk's tokens
     uint16_t     next_[WV_THREADS];             // subsequence the walk joined, 0xffff: the chain ends with thread t
     uint8_t      kind_[WV_THREADS];             // WK_*
     uint8_t      wlist[2][WV_THREADS];          // unfinished walks of a round, compacted
+    uint16_t     dpre_[WV_THREADS];             // deferred copies of the threads below t (exclusive prefix)
+    uint16_t     cst_[WV_THREADS];              // first list slot of thread t
+    uint32_t     dsum[WV_WARPS];
     uint32_t     wcount[3];
     uint32_t     bitmap[WV_BITMAP_WORDS];
     uint8_t      ring[WV_RING] __align__(16);
@@ -144,14 +149,16 @@ struct CopyItem { uint32_t o; uint32_t run_dist; };  // run | (dist - 1) << 16; 
 #ifdef PNGB200_EMU
 typedef uintptr_t saddr_t;
 inline uint32_t lds32(saddr_t addr) { return *(const uint32_t*)addr; }
-inline uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
-{
-    pos &= 0xff; len &= 0xff;   // PTX bfe.u32 semantics
-    if (len == 0 || pos > 31) return 0;
-    uint32_t v = x >> pos;
-    return len >= 32 ? v : v & ((1u << len) - 1u);
-}
+inline uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len);
 inline saddr_t smem_addr(const void* p) { return (uintptr_t)p; }
+inline uint32_t bmsk(uint32_t pos, uint32_t width)   // PTX bmsk.clamp.b32: `width` one bits starting at bit `pos`
+{
+    pos &= 0xff; width &= 0xff;
+    if (pos > 31 || width == 0) return 0;
+    const uint32_t m = width >= 32 ? ~0u : (1u << width) - 1u;
+    return m << pos;
+}
+inline uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len) { return pos > 31 ? 0 : (x >> pos) & bmsk(0, len); }
 #else
 typedef uint32_t saddr_t;
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
@@ -160,11 +167,17 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
+__device__ __forceinline__ uint32_t bmsk(uint32_t pos, uint32_t width)   // `width` one bits starting at bit `pos`
 {
     uint32_t r;
-    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pos), "r"(len));
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(pos), "r"(width));
     return r;
+}
+// bits [pos, pos + len) of x (pos <= 31).  sm_100 has no BFE instruction (ptxas expands bfe.u32 into five);
+// shift + BMSK + AND is three
+__device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
+{
+    return (x >> pos) & bmsk(0, len);
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 #endif
@@ -287,23 +300,38 @@ __device__ __forceinline__ uint32_t bit_mask(uint32_t lo, uint32_t hi)  // bits 
 {
     return (hi >= 32 ? ~0u : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
 }
-__device__ __forceinline__ void bits_clear(uint32_t* U, uint32_t a, uint32_t b)
+// set / clear / test the bits [o, o + run) (run >= 1): one or two words for run <= 32, the common case
+__device__ __forceinline__ void bits_set(uint32_t* U, uint32_t o, uint32_t run)
 {
-    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
-    if (wa == wb) { atomicAnd(U + wa, ~bit_mask(a & 31, ((b - 1) & 31) + 1)); return; }
-    atomicAnd(U + wa, ~bit_mask(a & 31, 32));
-    for (uint32_t w = wa + 1; w < wb; ++w) atomicAnd(U + w, 0u);
-    atomicAnd(U + wb, ~bit_mask(0, ((b - 1) & 31) + 1));
+    const uint32_t a = o & 31u;
+    uint32_t*      w = U + (o >> 5);
+    if (a + run <= 32u) { atomicOr(w, bmsk(a, run)); return; }
+    atomicOr(w, ~0u << a);
+    uint32_t rem = run - (32u - a);
+    for (++w; rem >= 32u; ++w, rem -= 32u) atomicOr(w, ~0u);
+    if (rem) atomicOr(w, bmsk(0, rem));
 }
-__device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t a, uint32_t b)
+__device__ __forceinline__ void bits_clear(uint32_t* U, uint32_t o, uint32_t run)
 {
-    const volatile uint32_t* V = U;
-    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    const uint32_t a = o & 31u;
+    uint32_t*      w = U + (o >> 5);
+    if (a + run <= 32u) { atomicAnd(w, ~bmsk(a, run)); return; }
+    atomicAnd(w, ~(~0u << a));
+    uint32_t rem = run - (32u - a);
+    for (++w; rem >= 32u; ++w, rem -= 32u) atomicAnd(w, 0u);
+    if (rem) atomicAnd(w, ~bmsk(0, rem));
+}
+__device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t o, uint32_t run)
+{
+    const volatile uint32_t* w = U + (o >> 5);
+    const uint32_t a = o & 31u;
     uint32_t any;
-    if (wa == wb) any = V[wa] & bit_mask(a & 31, ((b - 1) & 31) + 1);
+    if (a + run <= 32u) any = *w & bmsk(a, run);
     else {
-        any = (V[wa] & bit_mask(a & 31, 32)) | (V[wb] & bit_mask(0, ((b - 1) & 31) + 1));
-        for (uint32_t w = wa + 1; w < wb; ++w) any |= V[w];
+        any = *w & (~0u << a);
+        uint32_t rem = run - (32u - a);
+        for (++w; rem >= 32u; ++w, rem -= 32u) any |= *w;
+        if (rem) any |= *w & bmsk(0, rem);
     }
     __threadfence_block();
     return any == 0;
@@ -313,17 +341,20 @@ __device__ __forceinline__ bool bits_all_clear(const uint32_t* U, uint32_t a, ui
 // byte; the source is final or is produced by this very loop when the ranges overlap).
 __device__ __forceinline__ void ring_copy(uint8_t* ring, uint32_t d, uint32_t s, uint32_t run, uint32_t dist)
 {
-    if (dist >= 4) {  // byte k+3 reads k+3-dist < k: four independent loads per step even when overlapping
-        uint32_t k = 0;
-        for (; k + 4 <= run; k += 4) {
-            const uint8_t b0 = ring[(s + k) & 0xffffu], b1 = ring[(s + k + 1) & 0xffffu],
-                          b2 = ring[(s + k + 2) & 0xffffu], b3 = ring[(s + k + 3) & 0xffffu];
-            ring[(d + k) & 0xffffu] = b0;
-            ring[(d + k + 1) & 0xffffu] = b1;
-            ring[(d + k + 2) & 0xffffu] = b2;
-            ring[(d + k + 3) & 0xffffu] = b3;
+    d &= 0xffffu;
+    s &= 0xffffu;
+    if (dist >= 4 && max(d, s) + run + 3 < WV_RING) {
+        // four bytes per step: byte k+3 reads k+3-dist < k, so the loads of a step never depend on its stores;
+        // the loads may run up to 3 bytes past the run (still inside the ring), the stores may not
+        const uint8_t* sp = ring + s;
+        uint8_t*       dp = ring + d;
+        for (uint32_t k = 0; k < run; k += 4) {
+            const uint8_t b0 = sp[k], b1 = sp[k + 1], b2 = sp[k + 2], b3 = sp[k + 3];
+            dp[k] = b0;
+            if (k + 1 < run) dp[k + 1] = b1;
+            if (k + 2 < run) dp[k + 2] = b2;
+            if (k + 3 < run) dp[k + 3] = b3;
         }
-        for (; k < run; ++k) ring[(d + k) & 0xffffu] = ring[(s + k) & 0xffffu];
     } else {
         for (uint32_t k = 0; k < run; ++k) ring[(d + k) & 0xffffu] = ring[(s + k) & 0xffffu];
     }
@@ -358,50 +389,155 @@ struct EmitState {
     uint8_t*  hbm;       // HBM address of wave offset 0 (oversized waves write here directly)
     uint32_t* U;         // unresolved bitmap
     CopyItem* list;
-    uint64_t  out;       // stream offset of wave offset 0
+    uint32_t  reach;     // stream offset of wave offset 0 (saturated: 2^31 - 1 once the window is full)
     uint32_t  o;         // next output byte (wave-relative)
+    uint32_t  first;     // my first output byte: only I flag bytes of [first, o) before the resolve sweep
     uint32_t  clean;     // my bytes in [clean, o) are final
     uint32_t  c_next;    // my next list slot
-    uint32_t  mw, mbits; // pending unresolved-bit word
     bool      bad_ref;   // invalidStringReference seen
 };
 
 template <bool IN_HBM>
 __device__ __forceinline__ void emit_token(EmitState& S, uint32_t run, uint32_t dist, uint32_t is_copy)
 {
+    const uint32_t o = S.o;
     if (!is_copy) {
-        if (IN_HBM) S.hbm[S.o] = (uint8_t)run;
-        else S.ring[(S.rbase + S.o) & 0xffffu] = (uint8_t)run;
-        ++S.o;
+        if (IN_HBM) S.hbm[o] = (uint8_t)run;
+        else S.ring[(S.rbase + o) & 0xffffu] = (uint8_t)run;
+        S.o = o + 1;
         return;
     }
-    const uint32_t o = S.o;
-    if ((uint64_t)dist > S.out + o) {  // invalidStringReference: the serial decoder reports it
+    if (dist > S.reach + o) {  // invalidStringReference: the serial decoder reports it
         S.bad_ref = true;
         return;
     }
     const int32_t src = (int32_t)o - (int32_t)dist;
-    if (src + (int32_t)run <= 0 || src >= (int32_t)S.clean) {
+    bool final = src + (int32_t)run <= 0 || src >= (int32_t)S.clean;
+    if (!final && src >= (int32_t)S.first)   // inside my own bytes, below a deferred copy: final unless it overlaps one
+        final = bits_all_clear(S.U, (uint32_t)src, min(run, dist));
+    if (final) {
         // source is final: behind the wave (the window), or inside this thread's own finished bytes
         if (IN_HBM) hbm_copy(S.hbm, o, run, dist);
         else ring_copy(S.ring, S.rbase + o, S.rbase + o - dist, run, dist);
     } else {
-        // flag [o, o + run) as unresolved; words are flushed once, when left
-        for (uint32_t a = o, e2 = o + run; a < e2;) {
-            const uint32_t w = a >> 5;
-            if (w != S.mw) {
-                if (S.mbits) atomicOr(S.U + S.mw, S.mbits);
-                S.mw = w;
-                S.mbits = 0;
-            }
-            const uint32_t hi = min(e2, (w + 1) << 5);
-            S.mbits |= bit_mask(a & 31, ((hi - 1) & 31) + 1);
-            a = hi;
-        }
+        bits_set(S.U, o, run);                                      // [o, o + run) is unresolved
         S.list[S.c_next++] = CopyItem{o, run | (dist - 1) << 16};  // list is sorted by o
         S.clean = o + run;
     }
     S.o = o + run;
+}
+
+// Block header, fast path (warp 0): a valid header that lies completely inside the input.  The
+// code-length-code lengths are picked out lane-parallel, the code lengths themselves are decoded by
+// lane 0 with a register bit buffer over the staged words (this loop is the serial part of every
+// block: ~100 cycles per symbol instead of ~250 for the lock-step general parser).  Anything irregular
+// -- block type 3, a bad count, an invalid code-length code, a repeat without a predecessor, too many
+// lengths, truncation -- returns false and the caller runs parse_block_header, which owns the exact
+// error semantics of the reference (Stream.readBlockMetadata / readBlockTables,
+// LZ77.InflatorBuffers.Stream.swift:59-263).
+__device__ bool wv_fast_header(WvShared& sh, uint64_t hbase_bit, uint64_t pos, uint64_t total_bits, int lane, WvHeader& out)
+{
+    const uint32_t* const W = sh.words;
+    auto get = [&](uint32_t rel, uint32_t n) -> uint32_t {   // n <= 32 bits at staged bit `rel`
+        const uint32_t w = rel >> 5;
+        const uint32_t v = __funnelshift_r(W[w], W[w + 1], rel & 31u);
+        return n >= 32 ? v : v & ((1u << n) - 1u);
+    };
+    uint32_t rel = (uint32_t)(pos - hbase_bit);
+    if (pos + 3 > total_bits) return false;
+    const uint32_t h3 = get(rel, 3);
+    rel += 3;
+    out.status = PNGB200_OK;
+    out.final = (int32_t)(h3 & 1u);
+    out.type = (int32_t)(h3 >> 1);
+    out.stored = 0;
+    out.nlit = out.ndist = 0;
+    if (out.type == 3) return false;
+    if (out.type == 0) {
+        const uint64_t boundary = (pos + 3 + 7) & ~(uint64_t)7;
+        if (boundary + 32 > total_bits) return false;
+        const uint32_t v = get((uint32_t)(boundary - hbase_bit), 32);
+        const uint32_t l = v & 0xffffu, m = v >> 16;
+        if (l != (~m & 0xffffu)) return false;
+        out.stored = l;
+        out.pos = boundary + 32;
+        return true;
+    }
+    uint8_t* const lens = sh.ser.lens;
+    if (out.type == 1) {
+        for (int k = lane; k < 320; k += 32) lens[k] = k < 144 ? 8 : k < 256 ? 9 : k < 280 ? 7 : k < 288 ? 8 : 5;
+        out.nlit = 288;
+        out.ndist = 32;
+        out.pos = pos + 3;
+        __syncwarp();
+        return true;
+    }
+    if (pos + 17 > total_bits) return false;
+    const uint32_t v = get(rel, 14);
+    rel += 14;
+    const int nlit = 257 + (int)(v & 31u), ndist = 1 + (int)((v >> 5) & 31u), nclen = 4 + (int)(v >> 10);
+    if (nlit > 286) return false;
+    if (lane < 19) lens[lane] = 0;
+    __syncwarp();
+    if (lane < nclen) lens[c_clen_order[lane]] = (uint8_t)get(rel + 3u * (uint32_t)lane, 3);
+    rel += 3u * (uint32_t)nclen;
+    __syncwarp();
+    build_table<META_ROOT, META_CAP>(sh.ser.meta, lens, 19, ALPHA_META, &sh.ser.scratch, lane, 32);
+    if (sh.ser.scratch.status) return false;
+    __syncwarp();
+    uint32_t ok = 1, end_rel = 0;
+    if (lane == 0) {
+        const uint32_t* const meta = sh.ser.meta;
+        uint32_t wi  = rel >> 5;
+        uint64_t buf = ((uint64_t)W[wi + 1] << 32 | W[wi]) >> (rel & 31u);
+        int      cnt = 64 - (int)(rel & 31u);
+        wi += 2;
+        const int total = nlit + ndist;
+        int       have = 0;
+        uint32_t  prev = 0;
+        while (have < total) {
+            if (cnt < 32) {
+                buf |= (uint64_t)(wi < WV_HDR_WORDS ? W[wi] : 0u) << cnt;
+                cnt += 32;
+                ++wi;
+            }
+            const uint32_t e = meta[(uint32_t)buf & (META_CAP - 1)];
+            if (e & E_SPECIAL) { ok = 0; break; }
+            const uint32_t len = e & 15u, sym = e >> 16;
+            buf >>= len;
+            cnt -= (int)len;
+            if (sym < 16) {
+                lens[have++] = (uint8_t)sym;
+                prev = sym;
+                continue;
+            }
+            uint32_t element, extra, base;
+            if (sym == 16) {
+                if (have == 0) { ok = 0; break; }
+                element = prev; extra = 2; base = 3;
+            } else if (sym == 17) {
+                element = 0; extra = 3; base = 3;
+            } else {
+                element = 0; extra = 7; base = 11;
+            }
+            const int reps = (int)(base + ((uint32_t)buf & ((1u << extra) - 1u)));
+            buf >>= extra;
+            cnt -= (int)extra;
+            if (have + reps > total) { ok = 0; break; }
+            for (int k = 0; k < reps; ++k) lens[have + k] = (uint8_t)element;
+            prev = element;
+            have += reps;
+        }
+        end_rel = (wi << 5) - (uint32_t)cnt;
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    end_rel = __shfl_sync(0xffffffffu, end_rel, 0);
+    if (!ok || hbase_bit + end_rel > total_bits) return false;
+    out.nlit = nlit;
+    out.ndist = ndist;
+    out.pos = hbase_bit + end_rel;
+    __syncwarp();
+    return true;
 }
 
 // Adler-32 partial sums of bytes [0, n) at `p` for a piece whose first byte has weight `wt` (weights
@@ -521,12 +657,19 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                 for (uint32_t k = t; k < WV_HDR_WORDS; k += WV_THREADS) sh.words[k] = br.load_word(hbase + k);
                 __syncthreads();
                 if (warp == 0) {
-                    int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
-                    uint32_t stored0 = 0;
-                    StagedReader sr;
-                    sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
-                    int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
-                    if (lane == 0) sh.hdr = WvHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                    WvHeader h;
+                    if (!wv_fast_header(sh, hbase << 5, br.pos, br.total_bits, (int)lane, h)) {
+#ifdef PNGB200_EMU
+                        if (lane == 0 && getenv("WV_TRACE_HDR")) fprintf(stderr, "slow header at bit %llu\n", (unsigned long long)br.pos);
+#endif
+                        int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
+                        uint32_t stored0 = 0;
+                        StagedReader sr;
+                        sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
+                        int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
+                        h = WvHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                    }
+                    if (lane == 0) sh.hdr = h;
                 }
             }
             __syncthreads();
@@ -576,8 +719,7 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) mk[k * WV_THREADS + t] = 0;
-                        sh.ckn[t] = 0;
-                        sh.ckc[t] = 0;
+                        sh.ck[t] = 0;
                         FastBits b;
                         b.init(words_addr, t == 0 ? rel0 : base);
                         uint32_t mi = 0, mw = 0, n = 0;
@@ -586,11 +728,8 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                             if (wi != mi) {
                                 mk[mi * WV_THREADS + t] = mw;
                                 mw = 0;
-                                do {   // counts of the tokens that start before bit 32 * mi
-                                    ++mi;
-                                    sh.ckn[mi * WV_THREADS + t] = (uint16_t)nout;
-                                    sh.ckc[mi * WV_THREADS + t] = (uint8_t)ncopy;
-                                } while (mi != wi);
+                                mi = wi;
+                                sh.ck[wi * WV_THREADS + t] = nout | ncopy << 16;   // checkpoint of map word wi
                             }
                             mw |= 1u << (rr & 31);
                             uint32_t run = 0, dist = 0, cp = 0;
@@ -605,6 +744,7 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                         WV_COUNT(0, n);
                     }
                     sh.exit_[t] = exit_bit;
+                    sh.cross_[t] = 0;
                     __syncthreads();                                      // (2) maps complete
                     tick(2);
 
@@ -629,10 +769,18 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                                 FastBits b;
                                 b.init(words_addr, pos);
                                 uint32_t kind = WK_RUNNING;
+                                const uint32_t first_sub = sh.exit_[u] >> 8;
+                                bool     crossed = sh.cross_[u] != 0;
                                 for (; iters < K; ++iters) {
                                     const uint32_t p = b.pos;
                                     if (p >= WV_BITS) { kind = WK_END; break; }
                                     const uint32_t s = p >> 8, rr = p & 255u;
+                                    if (!crossed && s > first_sub) {
+                                        // a walk that leaves a subsequence without joining: the skipped owner
+                                        // can take the part of the walk that lies in its subsequence (phase D)
+                                        sh.cross_[u] = 1ull << 63 | (uint64_t)p << 40 | (uint64_t)(wc & 0xffu) << 24 | (wn & 0xffffffu);
+                                        crossed = true;
+                                    }
                                     if ((mk[(rr >> 5) * WV_THREADS + s] >> (rr & 31)) & 1u) { kind = WK_SYNC; break; }
                                     uint32_t run = 0, dist = 0, cp = 0;
                                     const uint32_t e = wv_decode<false>(b, lit, dstt, run, dist, cp);
@@ -717,8 +865,9 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     //      of my predecessor on the chain to my own exit (the last thread adds its own walk) ----
                     const bool     on_chain = (sh.valid[warp] >> lane) & 1u;
                     const uint32_t last = sh.last, term = sh.term;
-                    uint32_t from = rel0;            // where my share starts
+                    uint32_t from = rel0, to = exit_bit;   // my share of the chain: the tokens that start in [from, to)
                     uint32_t my_nout = 0, my_ncopy = 0;
+                    bool     adopted = false;              // not on the chain, but I take a piece of my left neighbour's walk
                     if (on_chain) {
                         uint32_t pn = 0, pc = 0, pre_n = 0, pre_c = 0;
                         if (t > 0) {
@@ -729,11 +878,22 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                             from = sh.exit_[pred];
                             pn = sh.wn_[pred];
                             pc = sh.wc_[pred];
+                            if (pred + 1 < t) {
+                                // the walk crossed the subsequences pred+1 .. t-1 without joining; thread pred+1
+                                // takes the tokens that start in its subsequence, I take the rest
+                                const uint64_t cr = sh.cross_[pred];
+                                if (cr) {
+                                    from = (uint32_t)(cr >> 40) & 0x1ffffu;
+                                    pn -= (uint32_t)cr & 0xffffffu;
+                                    pc -= (uint32_t)(cr >> 24) & 0xffu;
+                                }
+                            }
                             // my garbage prefix: tokens of mine that start before p0 = checkpoint of p0's map
                             // word + the tokens between the first start in that word and p0
                             const uint32_t rr = p0 - base, q = rr >> 5;
-                            pre_n = sh.ckn[q * WV_THREADS + t];
-                            pre_c = sh.ckc[q * WV_THREADS + t];
+                            const uint32_t ck = sh.ck[q * WV_THREADS + t];
+                            pre_n = ck & 0xffffu;
+                            pre_c = ck >> 16;
                             const uint32_t first = (uint32_t)__ffs((int)mk[q * WV_THREADS + t]) - 1;
                             if (first != (rr & 31)) {
                                 FastBits b;
@@ -749,11 +909,22 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                         my_nout  = pn + nout - pre_n;
                         my_ncopy = pc + ncopy - pre_c;
                         if (t == last) {
+                            to = wpos;
                             my_nout += sh.wn_[t];
                             my_ncopy += sh.wc_[t];
                             // ---- anomalies on the chain -> serial decoder ----
                             if (term == WK_BAD || term == WK_OWN_BAD || (wbase << 5) + wpos > br.total_bits)
                                 sh.anomaly = 1;
+                        }
+                    }
+                    else if (t > 0 && ((sh.valid[(t - 1) >> 5] >> ((t - 1) & 31)) & 1u) && sh.kind_[t - 1] == WK_SYNC) {
+                        const uint64_t cr = sh.cross_[t - 1];
+                        if (cr) {
+                            adopted  = true;
+                            from     = sh.exit_[t - 1];
+                            to       = (uint32_t)(cr >> 40) & 0x1ffffu;
+                            my_nout  = (uint32_t)cr & 0xffffffu;
+                            my_ncopy = (uint32_t)(cr >> 24) & 0xffu;
                         }
                     }
                     // ---- scan of output byte counts and copy counts (packed: copies << 40 | bytes) ----
@@ -799,12 +970,12 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     }
                     ring_stale = in_hbm;
                     uint32_t deferred = 0, emitted = 0;
-                    if (on_chain) {
+                    if (on_chain || adopted) {
                         EmitState S;
-                        S.ring = sh.ring; S.rbase = rbase; S.hbm = wdst; S.U = U; S.list = list; S.out = out;
-                        S.o = o_start; S.clean = o_start; S.c_next = c_start;
-                        S.mw = o_start >> 5; S.mbits = 0; S.bad_ref = false;
-                        const uint32_t to = t == last ? wpos : exit_bit;
+                        S.ring = sh.ring; S.rbase = rbase; S.hbm = wdst; S.U = U; S.list = list;
+                        S.reach = out >= WV_WINDOW ? 0x7fffffffu : (uint32_t)out;
+                        S.o = o_start; S.first = o_start; S.clean = o_start; S.c_next = c_start;
+                        S.bad_ref = false;
                         FastBits b;
                         b.init(words_addr, from);
                         if (in_hbm) {
@@ -822,58 +993,80 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                                 ++emitted;
                             }
                         }
-                        if (S.mbits) atomicOr(U + S.mw, S.mbits);
                         if (S.bad_ref) sh.anomaly = 1;
                         deferred = S.c_next - c_start;
-                        for (uint32_t c = S.c_next; c < c_start + my_ncopy; ++c) list[c] = CopyItem{0, 0};
                     }
                     WV_COUNT(2, emitted);
+                    // ---- F. resolve the deferred copies.  Their list is sparse (slots were handed out for ALL
+                    //      copies before anybody knew which ones would wait), so a scan of the per-thread counts
+                    //      numbers them densely in output order; item g lives in the region of the last thread
+                    //      whose prefix is <= g ----
+                    uint32_t dincl = deferred;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, dincl, o);
+                        if ((int)lane >= o) dincl += v;
+                    }
+                    if (lane == 31) sh.dsum[warp] = dincl;
                     __threadfence_block();
                     __syncthreads();                                      // (7)
                     tick(6);
-                    // ---- F. resolve: no CTA barriers.  The list is sorted by output offset and a copy only
-                    //      depends on smaller offsets, so a lane may simply block on its current item
-                    //      (items t, t + 256, ... in order): the smallest open item is always ready ----
-                    if (!sh.anomaly && np) {
-                        // the list lives in L2: the item after the current one is fetched while the current
-                        // one is being copied
-                        uint32_t idx  = t, rounds = 0;
-                        CopyItem it   = CopyItem{0, 0}, nxt = CopyItem{0, 0};
-                        bool     have = false, have_nxt = false;
-                        if (idx < np) {
-                            nxt = list[idx];
-                            idx += WV_THREADS;
-                            have_nxt = true;
+                    uint32_t nd = 0;
+                    {
+                        uint32_t below = 0;
+#pragma unroll
+                        for (int w = 0; w < WV_WARPS; ++w) {
+                            const uint32_t v = sh.dsum[w];
+                            below += w < (int)warp ? v : 0u;
+                            nd += v;
                         }
-                        for (;;) {
-                            if (!have && have_nxt) {
-                                it = nxt;
-                                have = (it.run_dist & 0xffff) != 0;   // empty slot: the copy ran inline
-                                have_nxt = idx < np;
-                                if (have_nxt) {
-                                    nxt = list[idx];
-                                    idx += WV_THREADS;
-                                }
+                        sh.dpre_[t] = (uint16_t)(below + dincl - deferred);
+                        sh.cst_[t]  = (uint16_t)c_start;
+                    }
+                    __syncthreads();                                      // (7b)
+                    // No CTA barriers from here.  The numbering is sorted by output offset and a copy only depends
+                    // on smaller offsets, so a lane may simply block on its current item (items t, t + 256, ...
+                    // in order): the smallest open item is always somebody's current item and it is ready.
+                    if (!sh.anomaly && nd) {
+                        auto slot_of = [&](uint32_t g) -> uint32_t {   // list slot of dense item g
+                            uint32_t lo = 0, hi = WV_THREADS;          // last u with dpre_[u] <= g
+                            while (hi - lo > 1) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (sh.dpre_[mid] <= g) lo = mid;
+                                else hi = mid;
                             }
+                            return (uint32_t)sh.cst_[lo] + g - sh.dpre_[lo];
+                        };
+                        uint32_t g = t, rounds = 0;
+                        CopyItem it = CopyItem{0, 0}, n1 = it, n2 = it;   // fetched from L2 two items ahead
+                        if (g < nd) it = list[slot_of(g)];
+                        if (g + WV_THREADS < nd) n1 = list[slot_of(g + WV_THREADS)];
+                        if (g + 2 * WV_THREADS < nd) n2 = list[slot_of(g + 2 * WV_THREADS)];
+                        for (;;) {
                             bool progressed = false;
-                            if (have) {
+                            if (g < nd) {
                                 const uint32_t run = it.run_dist & 0xffff, dist = (it.run_dist >> 16) + 1;
-                                const int64_t  src = (int64_t)it.o - (int64_t)dist;
-                                const int64_t  hi  = src + (int64_t)min(run, dist);
+                                const int32_t  src = (int32_t)it.o - (int32_t)dist;
+                                const int32_t  hi  = src + (int32_t)min(run, dist);
                                 bool ready = true;
-                                if (hi > 0) ready = bits_all_clear(U, (uint32_t)max(src, (int64_t)0), (uint32_t)hi);
+                                if (hi > 0) {
+                                    const uint32_t lo = (uint32_t)max(src, 0);
+                                    ready = bits_all_clear(U, lo, (uint32_t)hi - lo);
+                                }
                                 if (ready) {
                                     if (in_hbm) hbm_copy(wdst, it.o, run, dist);
                                     else ring_copy(sh.ring, rbase + it.o, rbase + it.o - dist, run, dist);
                                     __threadfence_block();
-                                    bits_clear(U, it.o, it.o + run);
-                                    have = false;
+                                    bits_clear(U, it.o, run);
+                                    g += WV_THREADS;
+                                    it = n1;
+                                    n1 = n2;
+                                    if (g + 2 * WV_THREADS < nd) n2 = list[slot_of(g + 2 * WV_THREADS)];
                                     progressed = true;
                                 }
                             }
                             ++rounds;
-                            if (!__any_sync(0xffffffffu, have || have_nxt)) break;
-                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(40);
+                            if (!__any_sync(0xffffffffu, g < nd)) break;
+                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(20);
                         }
                         resolve_rounds += rounds;
                         WV_COUNT(4, rounds);
