@@ -32,9 +32,9 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (width, height, sixteen, default batch per GPU, default unique images)
-    "8k-rgba8": (7680, 4320, False, 444, 2),
-    "1080p-rgba8": (1920, 1080, False, 1024, 16),
-    "8k-rgba16": (7680, 4320, True, 8, 2),
+    "8k-rgba8": (7680, 4320, False, 444, 8),
+    "1080p-rgba8": (1920, 1080, False, 1184, 64),
+    "8k-rgba16": (7680, 4320, True, 8, 8),
     "small": (512, 512, False, 64, 4),
 }
 
@@ -77,19 +77,27 @@ def make_corpus(args, pkg, ctx):
     import corpus
     w, h, sixteen, _, _ = WORKLOADS[args.workload]
     bpp = 8 if sixteen else 4
-    out = []
-    for i in range(args.unique):
+    from concurrent.futures import ThreadPoolExecutor
+
+    def synth(i):
         img = corpus.make(args.kind, w, h, i, sixteen) if args.kind == "photo" else corpus.make(args.kind, w, h, i)
-        storage = np.ascontiguousarray(img).tobytes()
+        return np.ascontiguousarray(img).tobytes()
+
+    def finish(storage, filtered):
+        comp = zlib.compress(filtered, args.level) if args.encoder == "zlib" or ctx is None else None
+        return dict(pixels=storage, adler=zlib.adler32(filtered), idat=comp, filtered_len=len(filtered),
+                    filtered=filtered if comp is None else None)
+
+    workers = max(1, min(args.unique, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    with ThreadPoolExecutor(max_workers=workers) as ex:  # numpy and zlib release the GIL
+        storages = list(ex.map(synth, range(args.unique)))
         if ctx is not None:
-            (filtered,) = pkg.filter_batch(ctx, [dict(pixels=storage, width=w, height=h, volume=8 * bpp,
-                                                      depth=16 if sixteen else 8)])
+            filtered = [pkg.filter_batch(ctx, [dict(pixels=st, width=w, height=h, volume=8 * bpp,
+                                                    depth=16 if sixteen else 8)])[0] for st in storages]
         else:
             from oracle import oracle
-            filtered = oracle.png_filter(storage, w, h, 8 * bpp, 16 if sixteen else 8)
-        comp = zlib.compress(filtered, args.level) if args.encoder == "zlib" or ctx is None else None
-        out.append(dict(pixels=storage, adler=zlib.adler32(filtered), idat=comp, filtered_len=len(filtered),
-                        filtered=filtered if comp is None else None))
+            filtered = list(ex.map(lambda st: oracle.png_filter(st, w, h, 8 * bpp, 16 if sixteen else 8), storages))
+        out = list(ex.map(finish, storages, filtered))
     if ctx is not None and args.encoder == "ref":
         got = pkg.deflate_batch(ctx, [it["filtered"] for it in out], args.encode_level)
         for it, (st, comp) in zip(out, got):
@@ -253,18 +261,26 @@ def main():
         descs[i].interlaced, descs[i].format = 0, 0
     L = ctx._lib
 
-    status_words = torch.zeros((B, 2), dtype=torch.int64, device="cuda")
-    gathered = [torch.empty_like(status_words) for _ in range(world)] if world > 1 else None
+    shard = importlib.import_module("swift-png_b200.shard")
+    gather_device = torch.device("cuda", local_rank)
+    comp_sizes = [d_idat[i % B].numel() for i in range(B)] * world  # every rank holds B jobs of the same sizes
+
+    def decode_my_shard(_indices):
+        ctx.check(L.pngb200_decode_batch_enqueue(ctx.handle, descs, B, pkg.MEM_DEVICE))
+        ctx.check(L.pngb200_decode_batch_finish(ctx.handle, descs, B))  # synchronises the library's stream
+        return [(descs[i].status, descs[i].checksum, descs[i].produced) for i in range(B)]
 
     def step_device():
-        ctx.check(L.pngb200_decode_batch_enqueue(ctx.handle, descs, B, pkg.MEM_DEVICE))
-        ctx.check(L.pngb200_decode_batch_finish(ctx.handle, descs, B))
-        if world > 1:
-            # the only collective of the path: every rank learns the whole batch's per-image
-            # (status, adler32) words; decoded pixels stay sharded on the GPU that produced them
-            status_words.copy_(torch.tensor([[descs[i].status, descs[i].checksum] for i in range(B)],
-                                            dtype=torch.int64), non_blocking=True)
-            dist.all_gather(gathered, status_words)
+        if world == 1:
+            decode_my_shard(None)
+            return
+        # the only collective of the path (swift-png_b200/shard.py): every rank learns the whole batch's
+        # per-image (status, adler32, produced) words; decoded pixels stay sharded on the GPU that produced
+        # them.  The gather is issued after this rank's kernels have finished (finish() synchronised) and
+        # its result is consumed on the host before the next step starts, so no NCCL kernel is co-resident
+        # with the next step's inflate kernel
+        rows = shard.run_sharded(comp_sizes, decode_my_shard, device=gather_device, equal_shards=B)
+        assert len(rows) == world * B and all(r[0] == 0 for r in rows), "a rank reported a failed image"
 
     def barrier():
         if world > 1:
@@ -308,10 +324,15 @@ def main():
     if not args.no_e2e:
         import psutil
         per_image = storage_bytes + max(len(it["idat"]) for it in items)
-        avail = psutil.virtual_memory().available
-        EB = min(B, args.e2e_batch) if args.e2e_batch else (B if per_image * B < (110 << 30) else max(8, (110 << 30) // per_image))
-        while EB > 8 and EB * per_image * 2.5 * max(world, 1) > avail:
-            EB //= 2  # pinned host staging for the whole batch must fit comfortably in host RAM
+        # Pinned host staging per rank: min(24 GiB, 40 % of the host memory that is free / ranks), decided ONCE
+        # on rank 0 and broadcast, so that every rank times the same sub-batch and 8 ranks cannot pin the box
+        # to death (r01 lost its 8-GPU run to 94 GB of pinned memory per rank)
+        budget = min(24 << 30, int(0.4 * psutil.virtual_memory().available / max(world, 1)))
+        EB = max(8, min(B, args.e2e_batch or B, budget // per_image))
+        if world > 1:
+            eb = torch.tensor([EB], dtype=torch.int64, device="cuda")
+            dist.broadcast(eb, 0)
+            EB = int(eb.item())
         full_B, B = B, EB
         if args.e2e_api == "files":
             import struct
@@ -326,8 +347,8 @@ def main():
                               b"".join(chunk(b"IDAT", z[o:o + 65544]) for o in range(0, len(z), 65544)) + chunk(b"IEND", b""))
         src_key = "file" if args.e2e_api == "files" else "idat"
         comp_total = sum(len(items[i % len(items)][src_key]) for i in range(B))
-        h_in = torch.empty(comp_total, dtype=torch.uint8).pin_memory()
-        h_out = torch.empty((B, storage_bytes), dtype=torch.uint8).pin_memory()
+        h_in = torch.empty(comp_total, dtype=torch.uint8, pin_memory=True)   # cudaHostAlloc directly: no pageable twin
+        h_out = torch.empty((B, storage_bytes), dtype=torch.uint8, pin_memory=True)
         hdescs = (pkg.PngDesc * B)() if args.e2e_api == "files" else (pkg.ImageDesc * B)()
         at = 0
         for i in range(B):

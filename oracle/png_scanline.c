@@ -161,7 +161,17 @@ int orc_png_decode(int format, const uint8_t* idat, size_t n, uint32_t w, uint32
 {
     size_t   need = orc_png_filtered_size(w, h, volume, interlaced);
     size_t   cap  = need + 65536; /* room to detect extraneous image data */
-    uint8_t* filtered = (uint8_t*)malloc(cap ? cap : 1);
+    /* the inflated stream lives in a per-thread scratch that is kept between calls: a fresh 100+ MB
+     * malloc per image means a page-fault storm when 64 host threads decode 8K images side by side,
+     * which says nothing about the algorithm (the reference's Inflator keeps its window buffer too) */
+    static __thread uint8_t* scratch = NULL;
+    static __thread size_t   scratch_cap = 0;
+    if (scratch_cap < cap) {
+        free(scratch);
+        scratch = (uint8_t*)malloc(cap ? cap : 1);
+        scratch_cap = scratch ? cap : 0;
+    }
+    uint8_t* filtered = scratch;
     orc_inflate(format, idat, n, filtered, cap, res);
     int st = res->status;
     if (st == ORC_ERR_OUTPUT_CAPACITY) st = ORC_ERR_PNG_EXTRANEOUS_IMAGE_DATA;
@@ -175,7 +185,6 @@ int orc_png_decode(int format, const uint8_t* idat, size_t n, uint32_t w, uint32
         else if (st == ORC_NEED_MORE_INPUT)
             st = ORC_ERR_PNG_INCOMPLETE_DATASTREAM; /* PNG.Context.swift:134-141 at IEND */
     }
-    free(filtered);
     return st;
 }
 

@@ -36,9 +36,10 @@
 // (Sources/LZ77/Inflator/LZ77.InflatorBuffers.Stream.swift:266-381, LZ77.InflatorOut.swift:124-140).
 #pragma once
 
-#include "inflate_serial.cuh"
+#include "inflate_wave.cuh"   // shared pieces: FastBits, fast_lookup, StagedReader, wv_fast_header, CopyItem
 
 namespace pngb200 {
+namespace par {
 
 // CTA shape (tunable at compile time; measured r01 on 1184 x 1080p: 512x2 171.9 ms, 384x3 142.7,
 // 256x4 131.2, 128x8 123.2 ms -- more, smaller CTAs hide each other's barrier phases; subsequences of
@@ -62,8 +63,6 @@ constexpr uint32_t PAR_OUT_BYTES    = PAR_O;                         // wave out
 constexpr uint32_t PAR_BITMAP_WORDS = PAR_OUT_BYTES / 32;
 constexpr uint32_t PAR_LIST_CAP     = PAR_THREADS * (PAR_SUB_BITS / 2);  // >= copies per wave (2 bits min each)
 constexpr uint64_t PAR_MAX_WAVE_OUT = (uint64_t)PAR_LIST_CAP * 258;
-
-enum : uint32_t { PF_EOB = 1, PF_BAD = 2 };
 
 struct ParHeader {  // block header as parsed by warp 0, broadcast to the CTA
     int32_t  status, type, final, nlit, ndist;
@@ -97,120 +96,6 @@ struct ParParams {
     uint64_t         scratch_stride;
     uint64_t         bitmap_words; // size of the HBM bitmap of each CTA
     int              count;
-};
-
-struct CopyItem { uint32_t o; uint32_t run_dist; };  // run | (dist - 1) << 16
-
-#ifdef PNGB200_EMU
-typedef uintptr_t saddr_t;
-inline uint32_t lds32(saddr_t addr) { return *(const uint32_t*)addr; }
-inline uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
-{
-    pos &= 0xff; len &= 0xff;   // PTX bfe.u32 semantics
-    if (len == 0 || pos > 31) return 0;
-    uint32_t v = x >> pos;
-    return len >= 32 ? v : v & ((1u << len) - 1u);
-}
-inline saddr_t smem_addr(const void* p) { return (uintptr_t)p; }
-#else
-typedef uint32_t saddr_t;
-__device__ __forceinline__ uint32_t lds32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len)
-{
-    uint32_t r;
-    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pos), "r"(len));
-    return r;
-}
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-#endif
-
-struct FastBits {
-    saddr_t  wbase;     // shared-memory address of the staged words
-    uint32_t wi;        // next word to fetch
-    uint32_t cur, nxt;
-    uint32_t off;       // < 32 at every peek
-    uint32_t pos;
-    __device__ __forceinline__ void init(saddr_t words_addr, uint32_t start)
-    {
-        wbase = words_addr;
-        const uint32_t W = start >> 5;
-        cur = lds32(wbase + ((W + (W >> 3)) << 2));
-        nxt = lds32(wbase + ((W + 1 + ((W + 1) >> 3)) << 2));
-        wi  = W + 2;
-        off = start & 31;
-        pos = start;
-    }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, off); }
-    __device__ __forceinline__ void skip(uint32_t n)  // n <= 32
-    {
-        off += n;
-        pos += n;
-        if (off >= 32) {
-            cur = nxt;
-            nxt = lds32(wbase + ((wi + (wi >> 3)) << 2));
-            ++wi;
-            off -= 32;
-        }
-    }
-};
-
-// one table lookup of the decode passes: root entry, subtable entry behind a pointer (rare)
-template <int ROOT>
-__device__ __forceinline__ uint32_t fast_lookup(saddr_t table_addr, uint32_t bits)
-{
-    uint32_t e = lds32(table_addr + ((bits & ((1u << ROOT) - 1u)) << 2));
-    if ((e & (E_SPECIAL | E_PTR | E_INVALID)) == (E_SPECIAL | E_PTR))
-        e = lds32(table_addr + (((e >> 16) + bfe32(bits, ROOT, e_skip(e) - ROOT)) << 2));
-    return e;
-}
-
-// Block headers are parsed out of a shared-memory copy of the next 768 bytes of the stream (a
-// dynamic header is at most 566 bytes), same interface as BitReader.
-constexpr uint32_t PAR_HDR_WORDS = 192;
-struct StagedReader {
-    const uint32_t* w;
-    uint64_t        base_bit, total_bits, pos;
-    uint32_t        wi;
-    uint64_t        buf;
-    int             cnt;
-    __device__ void init(const uint32_t* words, uint64_t base, uint64_t total, uint64_t p)
-    {
-        w = words; base_bit = base; total_bits = total;
-        seek(p);
-    }
-    __device__ void seek(uint64_t p)
-    {
-        pos = p;
-        wi  = (uint32_t)((p - base_bit) >> 5);
-        buf = 0;
-        cnt = 0;
-        refill();
-        int skip = (int)(p & 31);
-        buf >>= skip;
-        cnt -= skip;
-    }
-    __device__ __forceinline__ void refill()
-    {
-        while (cnt <= 32) {
-            buf |= (uint64_t)(wi < PAR_HDR_WORDS ? w[wi] : 0u) << cnt;
-            cnt += 32;
-            ++wi;
-        }
-    }
-    __device__ __forceinline__ uint32_t peek() const { return (uint32_t)buf; }
-    __device__ __forceinline__ void consume(int n) { buf >>= n; cnt -= n; pos += n; }
-    __device__ __forceinline__ uint32_t take(int n)
-    {
-        uint32_t v = (uint32_t)buf & (n >= 32 ? ~0u : ((1u << n) - 1u));
-        consume(n);
-        return v;
-    }
-    __device__ __forceinline__ bool have(uint64_t n) const { return pos + n <= total_bits; }
 };
 
 // sync-phase decode: symbol boundaries and output byte count only
@@ -248,10 +133,6 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
 }
 
 // ---- unresolved-byte bitmap (bit i = output byte i of the wave is not final yet) ----
-__device__ __forceinline__ uint32_t bit_mask(uint32_t lo, uint32_t hi)  // bits [lo, hi) of a word, hi <= 32
-{
-    return (hi >= 32 ? ~0u : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-}
 // spans of <= 33 bits touch at most two words: straight-line fast path, generic loop otherwise
 __device__ __forceinline__ void bits_set(uint32_t* U, uint32_t a, uint32_t b)
 {
@@ -372,15 +253,19 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
             __syncthreads();
             {
                 const uint64_t hbase = br.pos >> 5;
-                for (uint32_t k = t; k < PAR_HDR_WORDS; k += PAR_THREADS) sh.words[k] = br.load_word(hbase + k);
+                for (uint32_t k = t; k < WV_HDR_WORDS; k += PAR_THREADS) sh.words[k] = br.load_word(hbase + k);
                 __syncthreads();
                 if (warp == 0) {
-                    int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
-                    uint32_t stored0 = 0;
-                    StagedReader sr;
-                    sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
-                    int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
-                    if (lane == 0) sh.hdr = ParHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                    WvHeader h;
+                    if (!wv_fast_header(sh, hbase << 5, br.pos, br.total_bits, (int)lane, h)) {
+                        int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
+                        uint32_t stored0 = 0;
+                        StagedReader sr;
+                        sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
+                        int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
+                        h = WvHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                    }
+                    if (lane == 0) sh.hdr = ParHeader{h.status, h.type, h.final, h.nlit, h.ndist, h.stored, h.pos};
                 }
             }
             __syncthreads();
@@ -683,4 +568,15 @@ inline uint64_t par_scratch_stride(uint64_t bitmap_words)
     return (s + 255) / 256 * 256;
 }
 
+}  // namespace par
+using par::ParParams;
+using par::ParShared;
+using par::inflate_parallel_kernel;
+using par::PAR_THREADS;
+using par::PAR_CTAS_PER_SM;
+using par::par_bitmap_words;
+using par::par_scratch_stride;
+#ifndef PNGB200_EMU
+using par::configure_inflate_parallel;
+#endif
 }  // namespace pngb200

@@ -435,7 +435,8 @@ __device__ __forceinline__ void emit_token(EmitState& S, uint32_t run, uint32_t 
 // lengths, truncation -- returns false and the caller runs parse_block_header, which owns the exact
 // error semantics of the reference (Stream.readBlockMetadata / readBlockTables,
 // LZ77.InflatorBuffers.Stream.swift:59-263).
-__device__ bool wv_fast_header(WvShared& sh, uint64_t hbase_bit, uint64_t pos, uint64_t total_bits, int lane, WvHeader& out)
+template <class Shared>
+__device__ bool wv_fast_header(Shared& sh, uint64_t hbase_bit, uint64_t pos, uint64_t total_bits, int lane, WvHeader& out)
 {
     const uint32_t* const W = sh.words;
     auto get = [&](uint32_t rel, uint32_t n) -> uint32_t {   // n <= 32 bits at staged bit `rel`

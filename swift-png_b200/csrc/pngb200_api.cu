@@ -21,6 +21,7 @@
 #include "color.cuh"
 #include "crc32.cuh"
 #include "inflate_wave.cuh"
+#include "inflate_parallel.cuh"
 #include "inflate_serial.cuh"
 #include "unfilter.cuh"
 
@@ -192,29 +193,57 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
         if (!par.empty()) {
             uint64_t max_cap = 0;
             for (uint32_t i : par) max_cap = std::max<uint64_t>(max_cap, h_jobs[i].dst_cap);
-            WvParams pp;
-            pp.bitmap_words = wv_bitmap_words(max_cap);
-            pp.scratch_stride = wv_scratch_stride(pp.bitmap_words);
-            unsigned grid = (unsigned)std::min<size_t>(par.size(), (size_t)ctx->sm_count * WV_CTAS_PER_SM);
-            size_t need = (size_t)pp.scratch_stride * grid + 256;
-            // The per-CTA "unresolved" bitmaps must be all-zero when a launch starts; the kernel
-            // leaves them clean.  A different stride moves the bitmaps onto bytes that held copy
+            // Two engines for the big streams, same decomposition (8 KiB waves of 256 subsequences), chosen by
+            // how many streams there are to keep the SMs busy:
+            //  * inflate_wave_kernel: LZ77 window in a 64 KiB shared-memory ring, Adler-32 folded into the store;
+            //    2 CTAs per SM.  Fastest per stream (146 K cycles per wave against 234 K), so it takes every batch
+            //    that fits its 2 x SMs CTA slots -- and all multi-CTA-per-stream work.
+            //  * inflate_parallel_kernel (round 1): 16 KiB output image, window read back from HBM/L2, 4 CTAs per
+            //    SM.  Slower per stream, but twice the streams in flight hide its barrier phases: measured r02 on
+            //    8K RGBA8 1.96 ms per image against 2.51 ms once a batch exceeds the wave kernel's slots.
+            const size_t wave_slots = (size_t)ctx->sm_count * WV_CTAS_PER_SM;
+            bool use_wave = par.size() <= wave_slots;
+            if (ctx->inflate_mode == 3) use_wave = true;
+            if (ctx->inflate_mode == 4) use_wave = false;
+            const uint64_t bitmap_words = use_wave ? wv_bitmap_words(max_cap) : par_bitmap_words(max_cap);
+            const uint64_t stride = use_wave ? wv_scratch_stride(bitmap_words) : par_scratch_stride(bitmap_words);
+            unsigned grid = (unsigned)std::min<size_t>(par.size(), use_wave ? wave_slots : (size_t)ctx->sm_count * PAR_CTAS_PER_SM);
+            size_t need = (size_t)stride * grid + 256;
+            // The per-CTA "unresolved" bitmaps must be all-zero when a launch starts; the kernels
+            // leave them clean.  A different stride moves the bitmaps onto bytes that held copy
             // lists before, and a fresh allocation is garbage: zero the whole arena in both cases.
-            if (need > ctx->d_scratch.cap || pp.scratch_stride != ctx->scratch_stride) {
+            if (need > ctx->d_scratch.cap || stride != ctx->scratch_stride) {
                 CU(ctx->d_scratch.reserve(need));
                 CU(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, ctx->stream));
-                ctx->scratch_stride = pp.scratch_stride;
+                ctx->scratch_stride = stride;
             }
-            pp.ticket = (uint32_t*)((char*)ctx->d_scratch.p + (size_t)pp.scratch_stride * grid);
-            CU(cudaMemsetAsync(pp.ticket, 0, sizeof(uint32_t), ctx->stream));
-            pp.jobs = d_jobs;
-            pp.results = d_results;
-            pp.order = d_order;
-            pp.scratch = ctx->d_scratch.as<uint8_t>();
-            pp.count = (int)par.size();
+            uint32_t* ticket = (uint32_t*)((char*)ctx->d_scratch.p + (size_t)stride * grid);
+            CU(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), ctx->stream));
             if (int rc = before_first_launch()) return rc;
             hooked = true;
-            inflate_wave_kernel<<<grid, WV_THREADS, sizeof(WvShared), ctx->stream>>>(pp);
+            if (use_wave) {
+                WvParams pp;
+                pp.bitmap_words = bitmap_words;
+                pp.scratch_stride = stride;
+                pp.ticket = ticket;
+                pp.jobs = d_jobs;
+                pp.results = d_results;
+                pp.order = d_order;
+                pp.scratch = ctx->d_scratch.as<uint8_t>();
+                pp.count = (int)par.size();
+                inflate_wave_kernel<<<grid, WV_THREADS, sizeof(WvShared), ctx->stream>>>(pp);
+            } else {
+                ParParams pp;
+                pp.bitmap_words = bitmap_words;
+                pp.scratch_stride = stride;
+                pp.ticket = ticket;
+                pp.jobs = d_jobs;
+                pp.results = d_results;
+                pp.order = d_order;
+                pp.scratch = ctx->d_scratch.as<uint8_t>();
+                pp.count = (int)par.size();
+                inflate_parallel_kernel<<<grid, PAR_THREADS, sizeof(ParShared), ctx->stream>>>(pp);
+            }
             ctx->launches++;
         }
         if (!hooked)
@@ -479,6 +508,11 @@ pngb200_ctx* pngb200_ctx_create(int device)
     DeviceGuard guard(device);
     if (cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)) != cudaSuccess) {
         set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(DfShared));
+        delete ctx;
+        return nullptr;
+    }
+    if (configure_inflate_parallel() != 0) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(ParShared));
         delete ctx;
         return nullptr;
     }

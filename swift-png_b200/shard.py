@@ -28,15 +28,20 @@ def partition(sizes: Sequence[int], world: int) -> list[list[int]]:
 
 
 def run_sharded(sizes: Sequence[int], work: Callable[[list[int]], list[tuple[int, int, int]]],
-                group=None, device=None):
+                group=None, device=None, equal_shards: int = 0):
     """Each rank runs `work(my_indices)` -> [(status, checksum, produced)] and the results of the
     whole batch come back on every rank, in batch order.  `group`: a torch.distributed process
-    group (NCCL on GPUs, gloo in the CPU tests); None = single process."""
+    group (NCCL on GPUs, gloo in the CPU tests); None = single process.  `equal_shards` = n: the
+    batch is rank-major with n jobs per rank already (weak-scaling benchmark), no LPT needed."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if (group is not None or dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    shards = partition(sizes, world)
+    if equal_shards:
+        assert len(sizes) == equal_shards * world
+        shards = [list(range(r * equal_shards, (r + 1) * equal_shards)) for r in range(world)]
+    else:
+        shards = partition(sizes, world)
     mine = work(shards[rank])
     assert len(mine) == len(shards[rank])
     if world == 1:
