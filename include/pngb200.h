@@ -134,6 +134,13 @@ int          pngb200_ctx_inflate_stats(pngb200_ctx* ctx, size_t count, uint64_t 
  * inflate_wave_kernel as seen by thread 0 of each CTA: header+tables, stage, speculate, walk, chain,
  * count+scan, emit, resolve, store, stored blocks, (2 spare); out[20..23] reserved */
 int          pngb200_ctx_inflate_counters(pngb200_ctx* ctx, size_t count, uint64_t out[24]);
+/* more than one CTA per stream: a batch with fewer big streams than half the CTA slots has its streams cut at
+ * DEFLATE block boundaries and decoded segment by segment (csrc/inflate_segments.cuh).  Of the last inflate /
+ * decode batch on this context: out[0] streams that were cut, out[1] segments they were cut into, out[2] streams
+ * whose segments did not line up and that were decoded whole after all (results are identical either way). */
+int          pngb200_ctx_segment_stats(pngb200_ctx* ctx, uint64_t out[3]);
+/* inflate_mode: 0 automatic; 1 one warp per stream; 2 a whole CTA per stream, never cut; 3 / 4 force the
+ * ring-window / the round-1 intra-stream kernel; 5 as 0 */
 
 /* ---- batched one-shot entry points (the throughput path) ---- */
 

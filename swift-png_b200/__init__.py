@@ -223,6 +223,8 @@ def lib():
     L.pngb200_ctx_stage_ms.restype = C.c_int
     L.pngb200_ctx_inflate_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_inflate_stats.restype = C.c_int
+    L.pngb200_ctx_segment_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.pngb200_ctx_segment_stats.restype = C.c_int
     L.pngb200_ctx_inflate_counters.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_inflate_counters.restype = C.c_int
     L.pngb200_inflate_batch.argtypes = [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_int]
@@ -330,6 +332,12 @@ class Context:
         return dict(waves=out[0], walk_tokens=out[1], resolve_rounds=out[2], fallbacks=out[3], tokens=out[4],
                     matches=out[5], deferred_matches=out[6], blocks=out[7],
                     cycles={n: out[8 + i] for i, n in enumerate(names)})
+
+    def segment_stats(self):
+        """(streams cut into segments, segments, streams decoded whole after all) of the last batch"""
+        out = (C.c_uint64 * 3)()
+        self.check(self._lib.pngb200_ctx_segment_stats(self.handle, out))
+        return dict(streams=out[0], segments=out[1], fallbacks=out[2])
 
     def set_inflate_mode(self, mode: int):
         self._lib.pngb200_ctx_set_inflate_mode(self.handle, mode)

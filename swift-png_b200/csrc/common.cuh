@@ -24,6 +24,11 @@ struct StreamJob {
     uint64_t       start_out;   // bytes already produced before start_bit
     int32_t        format;      // pngb200_format
     int32_t        phase;       // where to resume: 0 stream header, 1 block header, 2 trailer
+    // segments of a stream that several CTAs decode side by side (inflate_wave_kernel only):
+    uint64_t       stop_bit;    // 0 = to the end of the stream; else stop at the first block boundary >= stop_bit
+    uint32_t       symbolic;    // 1: dst is uint16_t[dst_cap]; a byte copied from in front of the segment becomes
+                                // the marker 0x8000 | index into the 32 KiB window that precedes the segment
+    uint32_t       pad_;
 };
 
 struct StreamResult {

@@ -362,14 +362,15 @@ __device__ __forceinline__ void ring_copy(uint8_t* ring, uint32_t d, uint32_t s,
 
 // The same for an oversized wave, whose output and sources live in HBM (`hbm` = address of wave
 // offset 0; the source is final or produced by this very loop).
-__device__ __forceinline__ void hbm_copy(uint8_t* hbm, uint32_t o, uint32_t run, uint32_t dist)
+template <typename T>
+__device__ __forceinline__ void hbm_copy(T* hbm, uint32_t o, uint32_t run, uint32_t dist)
 {
-    uint8_t*       to   = hbm + o;
-    const uint8_t* from = to - dist;
+    T*       to   = hbm + o;
+    const T* from = to - dist;
     if (dist >= 4) {
         uint32_t k = 0;
         for (; k + 4 <= run; k += 4) {
-            const uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
+            const T b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3];
             to[k] = b0; to[k + 1] = b1; to[k + 2] = b2; to[k + 3] = b3;
         }
         for (; k < run; ++k) to[k] = from[k];
@@ -422,6 +423,42 @@ __device__ __forceinline__ void emit_token(EmitState& S, uint32_t run, uint32_t 
     } else {
         bits_set(S.U, o, run);                                      // [o, o + run) is unresolved
         S.list[S.c_next++] = CopyItem{o, run | (dist - 1) << 16};  // list is sorted by o
+        S.clean = o + run;
+    }
+    S.o = o + run;
+}
+
+// A token of a SEGMENT (a piece of a stream that starts at a block boundary somewhere inside it and is decoded
+// by its own CTA): the output is 16-bit symbols in HBM.  Bytes that an LZ77 copy takes from in front of the
+// segment are not known yet; they become markers 0x8000 | index into the 32 KiB window that precedes the
+// segment, travel through later copies like any other symbol, and are replaced once the segment in front
+// has been resolved (window_propagate_kernel / marker_resolve_kernel in inflate_segments.cuh).
+__device__ __forceinline__ void emit_token_sym(EmitState& S, uint32_t run, uint32_t dist, uint32_t is_copy)
+{
+    uint16_t* const h = reinterpret_cast<uint16_t*>(S.hbm);
+    uint32_t o = S.o;
+    if (!is_copy) {
+        h[o] = (uint16_t)run;
+        S.o = o + 1;
+        return;
+    }
+    const uint32_t have = S.reach + o;              // bytes of the segment in front of this copy (saturated)
+    if (dist > have) {
+        const uint32_t pre = min(dist - have, run);  // this many bytes come from in front of the segment
+        const uint32_t idx = WV_WINDOW - (dist - have);
+        for (uint32_t k = 0; k < pre; ++k) h[o + k] = (uint16_t)(0x8000u | (idx + k));
+        o += pre;
+        run -= pre;
+        if (run == 0) { S.o = o; return; }
+    }
+    const int32_t src = (int32_t)o - (int32_t)dist;
+    bool final = src + (int32_t)run <= 0 || src >= (int32_t)S.clean;
+    if (!final && src >= (int32_t)S.first) final = bits_all_clear(S.U, (uint32_t)src, min(run, dist));
+    if (final) {
+        hbm_copy(h, o, run, dist);
+    } else {
+        bits_set(S.U, o, run);
+        S.list[S.c_next++] = CopyItem{o, run | (dist - 1) << 16};
         S.clean = o + run;
     }
     S.o = o + run;
@@ -597,11 +634,13 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
         uint32_t phase  = (uint32_t)job.phase;
         uint64_t resume_bit = job.start_bit, resume_out = job.start_out;
         uint8_t* const dst = job.dst;
+        const bool     sym = job.symbolic != 0;       // segment: 16-bit symbols, always written straight to HBM
+        const uint32_t esz = sym ? 2u : 1u;
         const uint32_t mis = (uint32_t)((uintptr_t)dst & 15);  // ring position = stream offset + mis (mod 65536)
         bool fallback = false;
         bool ring_stale = job.start_out != 0;   // the ring does not hold the window [out - 32768, out)
         // running Adler-32 (thread 0): valid when this launch sees the stream from its first byte
-        const bool adler_on = job.start_out == 0;
+        const bool adler_on = job.start_out == 0 && !sym;
         uint32_t   s1 = 1, s2 = 0;
         uint64_t   pend_len = 0;       // a finished piece whose partial sums wait in sh.adler_*
         bool       pend = false;
@@ -689,7 +728,8 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                 if (!br.have(8 * (uint64_t)stored)) { st = PNGB200_NEED_MORE_INPUT; break; }
                 if (out + stored > job.dst_cap) { st = fail(r, PNGB200_ERR_OUTPUT_CAPACITY); break; }
                 const uint8_t* s = job.src + (br.at() >> 3);
-                for (uint32_t k = t; k < stored; k += WV_THREADS) dst[out + k] = s[k];
+                if (sym) for (uint32_t k = t; k < stored; k += WV_THREADS) reinterpret_cast<uint16_t*>(dst)[out + k] = s[k];
+                else for (uint32_t k = t; k < stored; k += WV_THREADS) dst[out + k] = s[k];
                 if (adler_on && stored) adler_hbm(s, stored);
                 if (stored) ring_stale = true;
                 out += stored;
@@ -959,8 +999,8 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     }
                     const uint32_t  total  = (uint32_t)total64;
                     // ---- E. emit: decode my share once more and write it ----
-                    uint8_t* const  wdst   = dst + out;           // HBM address of wave offset 0
-                    const bool      in_hbm = total > WV_OUT_BYTES;
+                    uint8_t* const  wdst   = dst + out * esz;     // HBM address of wave offset 0
+                    const bool      in_hbm = sym || total > WV_OUT_BYTES;
                     const uint32_t  rbase  = (uint32_t)(out + mis) & 0xffffu;  // ring position of wave offset 0
                     uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
                     if (!in_hbm && ring_stale) {
@@ -979,7 +1019,14 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                         S.bad_ref = false;
                         FastBits b;
                         b.init(words_addr, from);
-                        if (in_hbm) {
+                        if (sym) {
+                            while (b.pos != to && b.pos < WV_BITS + 64) {
+                                uint32_t run = 0, dist = 0, cp = 0;
+                                if (wv_decode<true>(b, lit, dstt, run, dist, cp)) break;
+                                emit_token_sym(S, run, dist, cp);
+                                ++emitted;
+                            }
+                        } else if (in_hbm) {
                             while (b.pos != to && b.pos < WV_BITS + 64) {
                                 uint32_t run = 0, dist = 0, cp = 0;
                                 if (wv_decode<true>(b, lit, dstt, run, dist, cp)) break;
@@ -1054,7 +1101,8 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                                     ready = bits_all_clear(U, lo, (uint32_t)hi - lo);
                                 }
                                 if (ready) {
-                                    if (in_hbm) hbm_copy(wdst, it.o, run, dist);
+                                    if (sym) hbm_copy(reinterpret_cast<uint16_t*>(wdst), it.o, run, dist);
+                                    else if (in_hbm) hbm_copy(wdst, it.o, run, dist);
                                     else ring_copy(sh.ring, rbase + it.o, rbase + it.o - dist, run, dist);
                                     __threadfence_block();
                                     bits_clear(U, it.o, run);
@@ -1130,6 +1178,7 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
             ++blocks;
             resume_bit = br.at();
             resume_out = out;
+            if (job.stop_bit && !final && br.at() >= job.stop_bit) break;   // end of my segment (the host checks ==)
             if (final) {
                 phase = 2;
                 st = read_trailer(br, job.format, r);
@@ -1173,7 +1222,15 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                 for (int k = 0; k < 12; ++k) r->stat_cycles[k] = sh.cyc[k];
             }
         }
-        if (fallback) {
+        if (fallback && sym) {
+            // a segment cannot go through the byte-wise serial decoder: report it, the host decodes the stream whole
+            if (t == 0) {
+                r->status = PNGB200_ERR_INTERNAL;
+                r->produced = out;
+                r->consumed_bits = br.at();
+                r->blocks = blocks;
+            }
+        } else if (fallback) {
             // the serial decoder redoes this block (and whatever follows) and owns the result record
             __syncthreads();
             if (warp == 0) serial_inflate(sh.ser, job, r, resume_bit, resume_out, 1, blocks);

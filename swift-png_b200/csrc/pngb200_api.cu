@@ -22,6 +22,8 @@
 #include "crc32.cuh"
 #include "inflate_wave.cuh"
 #include "inflate_parallel.cuh"
+#include "block_search.cuh"
+#include "inflate_segments.cuh"
 #include "inflate_serial.cuh"
 #include "unfilter.cuh"
 
@@ -99,9 +101,10 @@ struct pngb200_ctx {
     int          pending_memspace = 0;
     // device workspaces (grow-only)
     DevBuf d_jobs, d_results, d_imgjobs, d_genjobs, d_misc, d_partial, d_filtered, d_in, d_out, d_order, d_scratch, d_dfscratch, d_dfjobs, d_dfres, d_enc,
-           d_file, d_crc, d_seg, d_crctab;
+           d_file, d_crc, d_seg, d_crctab, d_sgjobs, d_sgres, d_sgsym, d_sgsearch, d_sgrec, d_sgwin;
     // pinned host tables
-    PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order, h_crc, h_seg;
+    PinBuf h_jobs, h_results, h_imgjobs, h_genjobs, h_misc, h_order, h_crc, h_seg, h_sgsearch, h_sgjobs, h_sgres, h_sgrec;
+    uint64_t seg_streams = 0, seg_segments = 0, seg_fallbacks = 0;  // last batch: streams cut into segments, segments, rejected
     uint64_t scratch_stride = 0;       // layout of d_scratch the last inflate launch used
     size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // decode stage boundaries
@@ -154,12 +157,200 @@ struct DeviceGuard {
     }
 };
 
+// ---- more than one CTA per stream (inflate_segments.cuh) ----
+// Streams of `par` that are worth cutting are decoded here, segment by segment; on return `par` holds the
+// streams that still have to go through the whole-stream kernels (not cut, or a segment did not line up).
+// Two host round trips (split points, segment results): the path exists for batches that would otherwise
+// leave most of the GPU idle.
+int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t>& par)
+{
+    ctx->seg_streams = ctx->seg_segments = ctx->seg_fallbacks = 0;
+    const size_t slots = (size_t)ctx->sm_count * WV_CTAS_PER_SM;
+    constexpr uint64_t kMinSegment = 256u << 10;  // compressed bytes per segment, at least
+    if (par.empty() || par.size() * 2 > slots) return PNGB200_OK;
+    const size_t per_stream = std::max<size_t>(1, slots / par.size());
+    struct Cut { uint32_t stream; uint32_t nseg; size_t first_search; };
+    std::vector<Cut> cuts;
+    size_t nsearch = 0;
+    for (uint32_t i : par) {
+        const size_t nseg = std::min<size_t>(per_stream, h_jobs[i].src_len / kMinSegment);
+        if (nseg < 2 || h_jobs[i].start_bit != 0 || h_jobs[i].phase != 0 || h_jobs[i].dst_cap < (1u << 20)) continue;
+        cuts.push_back(Cut{i, (uint32_t)nseg, nsearch});
+        nsearch += nseg - 1;
+    }
+    if (cuts.empty()) return PNGB200_OK;
+    // 1. split points: the first plausible dynamic-block header at or after k / nseg of the stream
+    CU(ctx->h_sgsearch.reserve(sizeof(SearchJob) * nsearch));
+    CU(ctx->d_sgsearch.reserve(sizeof(SearchJob) * nsearch));
+    SearchJob* sj = ctx->h_sgsearch.as<SearchJob>();
+    for (const Cut& c : cuts) {
+        const StreamJob& j = h_jobs[c.stream];
+        const uint64_t bits = 8 * j.src_len, step = bits / c.nseg;
+        for (uint32_t k = 1; k < c.nseg; ++k) {
+            SearchJob& q = sj[c.first_search + k - 1];
+            q.src = j.src;
+            q.src_len = j.src_len;
+            q.from_bit = k * step;
+            q.limit_bit = k + 1 < c.nseg ? (k + 1) * step : bits;
+            q.found = ~0ull;
+        }
+    }
+    CU(cudaMemcpyAsync(ctx->d_sgsearch.p, sj, sizeof(SearchJob) * nsearch, cudaMemcpyHostToDevice, ctx->stream));
+    block_search_kernel<<<(unsigned)nsearch, 256, 0, ctx->stream>>>(ctx->d_sgsearch.as<SearchJob>(), (uint32_t)nsearch);
+    ctx->launches++;
+    CU(cudaMemcpyAsync(sj, ctx->d_sgsearch.p, sizeof(SearchJob) * nsearch, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // 2. one job per segment; symbols go to a scratch sized 1.5 x the segment's share of the output bound
+    std::vector<StreamJob> sg;
+    std::vector<uint32_t>  sg_stream, first_of;   // stream of each segment; first segment of each cut (+ end)
+    size_t sym_total = 0;
+    uint64_t max_cap = 0;
+    for (const Cut& c : cuts) {
+        const StreamJob& j = h_jobs[c.stream];
+        std::vector<uint64_t> at{0};
+        for (uint32_t k = 1; k < c.nseg; ++k)
+            if (sj[c.first_search + k - 1].found != ~0ull) at.push_back(sj[c.first_search + k - 1].found);
+        first_of.push_back((uint32_t)sg.size());
+        for (size_t k = 0; k < at.size(); ++k) {
+            const uint64_t end = k + 1 < at.size() ? at[k + 1] : 8 * j.src_len;
+            StreamJob s = j;
+            s.start_bit = at[k];
+            s.start_out = 0;
+            s.phase = k == 0 ? 0 : 1;
+            s.stop_bit = k + 1 < at.size() ? at[k + 1] : 0;
+            s.symbolic = 1;
+            s.dst_cap = (uint64_t)((double)j.dst_cap * 1.5 * (double)(end - at[k]) / (double)(8 * j.src_len)) + (64u << 10);
+            s.dst = (uint8_t*)(uintptr_t)sym_total;  // offset for now (symbols)
+            sym_total += align_up(s.dst_cap + 8, 128);
+            max_cap = std::max(max_cap, s.dst_cap);
+            sg.push_back(s);
+            sg_stream.push_back(c.stream);
+        }
+    }
+    first_of.push_back((uint32_t)sg.size());
+    const size_t n = sg.size();
+    CU(ctx->d_sgsym.reserve(sizeof(uint16_t) * sym_total));
+    for (StreamJob& s : sg) s.dst = (uint8_t*)(ctx->d_sgsym.as<uint16_t>() + (size_t)(uintptr_t)s.dst);
+    CU(ctx->h_sgjobs.reserve(sizeof(StreamJob) * n));
+    CU(ctx->d_sgjobs.reserve(sizeof(StreamJob) * n));
+    CU(ctx->d_sgres.reserve(sizeof(StreamResult) * n));
+    CU(ctx->h_sgres.reserve(sizeof(StreamResult) * n));
+    memcpy(ctx->h_sgjobs.p, sg.data(), sizeof(StreamJob) * n);
+    CU(cudaMemcpyAsync(ctx->d_sgjobs.p, ctx->h_sgjobs.p, sizeof(StreamJob) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_sgres.p, 0, sizeof(StreamResult) * n, ctx->stream));
+    {
+        WvParams pp;
+        pp.bitmap_words = wv_bitmap_words(max_cap);
+        pp.scratch_stride = wv_scratch_stride(pp.bitmap_words);
+        unsigned grid = (unsigned)std::min<size_t>(n, slots);
+        size_t need = (size_t)pp.scratch_stride * grid + 256;
+        if (need > ctx->d_scratch.cap || pp.scratch_stride != ctx->scratch_stride) {
+            CU(ctx->d_scratch.reserve(need));
+            CU(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, ctx->stream));
+            ctx->scratch_stride = pp.scratch_stride;
+        }
+        pp.ticket = (uint32_t*)((char*)ctx->d_scratch.p + (size_t)pp.scratch_stride * grid);
+        CU(cudaMemsetAsync(pp.ticket, 0, sizeof(uint32_t), ctx->stream));
+        pp.jobs = ctx->d_sgjobs.as<StreamJob>();
+        pp.results = ctx->d_sgres.as<StreamResult>();
+        pp.order = nullptr;
+        pp.scratch = ctx->d_scratch.as<uint8_t>();
+        pp.count = (int)n;
+        inflate_wave_kernel<<<grid, WV_THREADS, sizeof(WvShared), ctx->stream>>>(pp);
+        ctx->launches++;
+    }
+    CU(cudaMemcpyAsync(ctx->h_sgres.p, ctx->d_sgres.p, sizeof(StreamResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // 3. a stream is accepted when every segment ended exactly where the next one starts
+    const StreamResult* sr = ctx->h_sgres.as<StreamResult>();
+    std::vector<SegmentRecord> recs;
+    std::vector<uint32_t> stream_first{0};
+    std::vector<uint64_t> chunk_base;
+    std::vector<uint32_t> accepted;
+    std::vector<StreamResult> finals;
+    uint64_t chunks = 0;
+    for (size_t c = 0; c < cuts.size(); ++c) {
+        const uint32_t lo = first_of[c], hi = first_of[c + 1];
+        const StreamJob& j = h_jobs[cuts[c].stream];
+        bool ok = true;
+        uint64_t total = 0, blocks = 0;
+        for (uint32_t k = lo; k < hi && ok; ++k) {
+            const bool last = k + 1 == hi;
+            ok = sr[k].status == PNGB200_OK && (last ? sr[k].phase == 2 : (sr[k].phase == 1 && sr[k].consumed_bits == sg[k].stop_bit));
+            total += sr[k].produced;
+            blocks += sr[k].blocks;
+        }
+        if (ok && total > j.dst_cap) ok = false;
+        ctx->seg_streams++;
+        ctx->seg_segments += hi - lo;
+        if (!ok) { ctx->seg_fallbacks++; continue; }
+        uint64_t off = 0;
+        for (uint32_t k = lo; k < hi; ++k) {
+            SegmentRecord rec;
+            rec.sym = (const uint16_t*)sg[k].dst;
+            rec.out = j.dst + off;
+            rec.produced = sr[k].produced;
+            rec.stream = cuts[c].stream;
+            rec.first = k == lo;
+            chunk_base.push_back(chunks);
+            chunks += (sr[k].produced + 4095) / 4096;
+            off += sr[k].produced;
+            recs.push_back(rec);
+        }
+        stream_first.push_back((uint32_t)recs.size());
+        accepted.push_back(cuts[c].stream);
+        StreamResult f = sr[hi - 1];   // trailer fields come from the last segment
+        f.produced = total;
+        f.blocks = (uint32_t)blocks;
+        f.resume_out = total;
+        f.ck_done = 0;
+        f.stat_waves = 0;
+        for (uint32_t k = lo; k < hi; ++k) f.stat_waves += sr[k].stat_waves;
+        finals.push_back(f);
+    }
+    if (!recs.empty()) {
+        // 4. windows in front of the segments, then markers -> bytes at their final places
+        const size_t nr = recs.size(), ns = stream_first.size() - 1;
+        const size_t off_first = align_up(sizeof(SegmentRecord) * nr, 256);
+        const size_t off_chunk = align_up(off_first + sizeof(uint32_t) * (ns + 1), 256);
+        const size_t table = off_chunk + sizeof(uint64_t) * nr;
+        CU(ctx->h_sgrec.reserve(table));
+        CU(ctx->d_sgrec.reserve(table));
+        memcpy(ctx->h_sgrec.p, recs.data(), sizeof(SegmentRecord) * nr);
+        memcpy((char*)ctx->h_sgrec.p + off_first, stream_first.data(), sizeof(uint32_t) * (ns + 1));
+        memcpy((char*)ctx->h_sgrec.p + off_chunk, chunk_base.data(), sizeof(uint64_t) * nr);
+        CU(cudaMemcpyAsync(ctx->d_sgrec.p, ctx->h_sgrec.p, table, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx->d_sgwin.reserve((size_t)SEG_WINDOW * nr));
+        const SegmentRecord* d_recs = ctx->d_sgrec.as<SegmentRecord>();
+        window_propagate_kernel<<<(unsigned)ns, 256, 0, ctx->stream>>>(d_recs, (const uint32_t*)((char*)ctx->d_sgrec.p + off_first),
+                                                                       (uint32_t)ns, ctx->d_sgwin.as<uint8_t>());
+        if (chunks)
+            marker_resolve_kernel<<<(unsigned)chunks, 256, 0, ctx->stream>>>(d_recs, (uint32_t)nr, ctx->d_sgwin.as<uint8_t>(),
+                                                                             (const uint64_t*)((char*)ctx->d_sgrec.p + off_chunk));
+        ctx->launches += 2;
+        CU(cudaGetLastError());
+        // the streams' result records (the whole-stream kernels will not touch them)
+        StreamResult* d_results = ctx->d_results.as<StreamResult>();
+        StreamResult* hf = ctx->h_sgres.as<StreamResult>();  // reuse: the segment results have been consumed
+        for (size_t a = 0; a < accepted.size(); ++a) {
+            hf[a] = finals[a];
+            CU(cudaMemcpyAsync(d_results + accepted[a], hf + a, sizeof(StreamResult), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        std::vector<uint32_t> rest;
+        for (uint32_t i : par)
+            if (std::find(accepted.begin(), accepted.end(), i) == accepted.end()) rest.push_back(i);
+        par.swap(rest);
+    }
+    return PNGB200_OK;
+}
+
 // ---- inflate (+ checksum) over a device-resident job table ----
 // h_jobs: host copy (for dst_cap based chunk layout); d_jobs/d_results device arrays of `count`.
 int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
 {
     StreamJob*    d_jobs    = ctx->d_jobs.as<StreamJob>();
     StreamResult* d_results = ctx->d_results.as<StreamResult>();
+    ctx->seg_streams = ctx->seg_segments = ctx->seg_fallbacks = 0;
     CU(cudaMemsetAsync(d_results, 0, sizeof(StreamResult) * count, ctx->stream));
     auto before_first_launch = [&]() -> int {
         int rc = PNGB200_OK;
@@ -190,6 +381,20 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
         CU(cudaMemcpyAsync(ctx->d_order.p, ho, sizeof(uint32_t) * count, cudaMemcpyHostToDevice, ctx->stream));
         const uint32_t* d_order = ctx->d_order.as<uint32_t>();
         bool hooked = false;
+        if (ctx->inflate_mode == 0 || ctx->inflate_mode == 5) {
+            // few big streams: cut them so that every CTA slot has something to decode
+            const size_t before = par.size();
+            if (!par.empty() && par.size() * 2 <= (size_t)ctx->sm_count * WV_CTAS_PER_SM) {
+                if (int rc = before_first_launch()) return rc;
+                hooked = true;
+                if (int rc = run_segments(ctx, h_jobs, par)) return rc;
+            }
+            if (par.size() != before) {   // the order table lists what is left for the whole-stream kernels
+                std::copy(par.begin(), par.end(), ho);
+                std::copy(ser.begin(), ser.end(), ho + par.size());
+                CU(cudaMemcpyAsync(ctx->d_order.p, ho, sizeof(uint32_t) * (par.size() + ser.size()), cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
         if (!par.empty()) {
             uint64_t max_cap = 0;
             for (uint32_t i : par) max_cap = std::max<uint64_t>(max_cap, h_jobs[i].dst_cap);
@@ -219,7 +424,8 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             }
             uint32_t* ticket = (uint32_t*)((char*)ctx->d_scratch.p + (size_t)stride * grid);
             CU(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), ctx->stream));
-            if (int rc = before_first_launch()) return rc;
+            if (!hooked)
+                if (int rc = before_first_launch()) return rc;
             hooked = true;
             if (use_wave) {
                 WvParams pp;
@@ -539,9 +745,11 @@ void pngb200_ctx_destroy(pngb200_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->d_jobs, &ctx->d_results, &ctx->d_imgjobs, &ctx->d_genjobs, &ctx->d_misc,
                       &ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_order, &ctx->d_scratch, &ctx->d_dfscratch,
-                      &ctx->d_dfjobs, &ctx->d_dfres, &ctx->d_enc, &ctx->d_file, &ctx->d_crc, &ctx->d_seg, &ctx->d_crctab})
+                      &ctx->d_dfjobs, &ctx->d_dfres, &ctx->d_enc, &ctx->d_file, &ctx->d_crc, &ctx->d_seg, &ctx->d_crctab,
+                      &ctx->d_sgjobs, &ctx->d_sgres, &ctx->d_sgsym, &ctx->d_sgsearch, &ctx->d_sgrec, &ctx->d_sgwin})
         b->release();
-    for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order, &ctx->h_crc, &ctx->h_seg})
+    for (PinBuf* b : {&ctx->h_jobs, &ctx->h_results, &ctx->h_imgjobs, &ctx->h_genjobs, &ctx->h_misc, &ctx->h_order, &ctx->h_crc, &ctx->h_seg,
+                      &ctx->h_sgsearch, &ctx->h_sgjobs, &ctx->h_sgres, &ctx->h_sgrec})
         b->release();
     for (cudaEvent_t e : ctx->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -555,7 +763,7 @@ int pngb200_ctx_trim(pngb200_ctx* ctx)
     for (pngb200_ctx* lane : ctx->lanes) pngb200_ctx_trim(lane);
     DeviceGuard guard(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
-    for (DevBuf* b : {&ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_scratch, &ctx->d_dfscratch, &ctx->d_enc, &ctx->d_file})
+    for (DevBuf* b : {&ctx->d_partial, &ctx->d_filtered, &ctx->d_in, &ctx->d_out, &ctx->d_scratch, &ctx->d_dfscratch, &ctx->d_enc, &ctx->d_file, &ctx->d_sgsym, &ctx->d_sgwin})
         b->release();
     ctx->scratch_stride = 0;
     return PNGB200_OK;
@@ -603,6 +811,15 @@ int pngb200_ctx_inflate_counters(pngb200_ctx* ctx, size_t count, uint64_t out[24
         out[7] += r[i].blocks;
         for (int k = 0; k < 12; ++k) out[8 + k] += r[i].stat_cycles[k];
     }
+    return PNGB200_OK;
+}
+
+int pngb200_ctx_segment_stats(pngb200_ctx* ctx, uint64_t out[3])
+{
+    if (!ctx || !out) return PNGB200_ERR_BAD_ARGUMENT;
+    out[0] = ctx->seg_streams;
+    out[1] = ctx->seg_segments;
+    out[2] = ctx->seg_fallbacks;
     return PNGB200_OK;
 }
 
@@ -658,6 +875,9 @@ int pngb200_inflate_batch(pngb200_ctx* ctx, pngb200_stream_desc* s, size_t count
         jobs[i].start_out = 0;
         jobs[i].format = s[i].format;
         jobs[i].phase = 0;
+        jobs[i].stop_bit = 0;
+        jobs[i].symbolic = 0;
+        jobs[i].pad_ = 0;
     }
     CU(cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(StreamJob) * count, cudaMemcpyHostToDevice, ctx->stream));
     int rc = run_inflate(ctx, jobs, count);
@@ -738,6 +958,9 @@ int pngb200_decode_batch_enqueue(pngb200_ctx* ctx, pngb200_image_desc* im, size_
         jobs[i].start_out = 0;
         jobs[i].format = im[i].format;
         jobs[i].phase = 0;
+        jobs[i].stop_bit = 0;
+        jobs[i].symbolic = 0;
+        jobs[i].pad_ = 0;
     }
     CU(cudaMemcpyAsync(ctx->d_jobs.p, jobs, sizeof(StreamJob) * count, cudaMemcpyHostToDevice, ctx->stream));
     int rc = run_inflate(ctx, jobs, count);
@@ -1288,6 +1511,9 @@ int pngb200_inflator_push(pngb200_inflator* z, const uint8_t* data, size_t n)
         job->start_out = z->resume_out;
         job->format = z->format;
         job->phase = (int32_t)z->phase;
+        job->stop_bit = 0;
+        job->symbolic = 0;
+        job->pad_ = 0;
         CU(cudaMemcpyAsync(z->d_job.p, job, sizeof(StreamJob), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(z->d_res.p, 0, sizeof(StreamResult), ctx->stream));
         inflate_serial_kernel<<<1, 32, 0, ctx->stream>>>(z->d_job.as<StreamJob>(), z->d_res.as<StreamResult>(), nullptr, 1);

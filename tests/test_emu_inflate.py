@@ -139,3 +139,74 @@ def test_tiny_and_empty(lib):
         z = zlib.compress(plain, 6)
         st, got, r = run(lib, z, len(plain) + 8)
         assert st == 0 and got == plain and r.checksum == zlib.adler32(plain)
+
+
+# ---- more than one CTA per stream: block search + symbolic segments + window propagation + marker resolve ----
+@pytest.fixture(scope="module")
+def seglib():
+    L = emu.load("emu_inflate_segments")
+    L.emu_inflate_segmented.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64,
+                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    return L
+
+
+def run_segmented(L, z: bytes, plain_len: int, nseg: int, fmt: int = ZLIB, plant: int = 0):
+    src = (C.c_uint8 * (len(z) + 8)).from_buffer_copy(z + b"\0" * 8)
+    out = (C.c_uint8 * (plain_len + 64))()
+    prod, used = C.c_uint64(), C.c_uint32()
+    rc = L.emu_inflate_segmented(C.addressof(src), len(z), C.addressof(out), plain_len, fmt, nseg, plant,
+                                 C.byref(prod), C.byref(used))
+    return rc, bytes(out)[: prod.value], used.value
+
+
+@pytest.mark.parametrize("nseg", [2, 5])
+def test_segments_photo(seglib, nseg):
+    filt, z = photo_stream(512, 300)
+    rc, got, used = run_segmented(seglib, z, len(filt), nseg)
+    assert rc == 0 and got == filt and used == nseg
+
+
+def test_segments_markers_travel_through_long_copies(seglib):
+    """flat graphics: almost every byte of a segment is a copy of a copy of ... the window in front of it"""
+    img = corpus.make("graphic", 1400, 900, 2)
+    filt, _ = corpus.zlib_png_stream(img, 4, 6)
+    plain = filt[:300_000] * 5   # the same compression ratio everywhere: the segments' symbol buffers are sized by share
+    co = zlib.compressobj(6, zlib.DEFLATED, 15, 9)
+    z = b""
+    for o in range(0, len(plain), 50_000):   # a block boundary every 50 000 bytes
+        z += co.compress(plain[o:o + 50_000]) + co.flush(zlib.Z_SYNC_FLUSH)
+    z += co.flush()
+    rc, got, used = run_segmented(seglib, z, len(plain), 4)
+    assert rc == 0 and got == plain and used >= 2
+
+
+def test_segments_reference_stream_and_gzip(seglib):
+    filt, _ = photo_stream(400, 300)
+    z = oracle.deflate(filt, 9)        # few, growing blocks: not every split point finds a boundary
+    rc, got, used = run_segmented(seglib, z, len(filt), 6)
+    assert rc == 0 and got == filt and 1 <= used <= 6
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    z = co.compress(filt) + co.flush()
+    rc, got, used = run_segmented(seglib, z, len(filt), 3, fmt=GZIP)
+    assert rc == 0 and got == filt
+
+
+def test_segments_false_split_point_is_rejected(seglib):
+    """a split point that is not a block boundary (here: forged) must send the stream to the whole-stream path"""
+    filt, z = photo_stream(512, 300)
+    rc, _, _ = run_segmented(seglib, z, len(filt), 2, plant=8 * (len(z) // 3) + 3)
+    assert rc == 1
+
+
+def test_block_search_ignores_header_lookalike_in_stored_data(seglib):
+    """a complete dynamic-block header copied into a stored block: the search may find it, the chain check must
+    then reject the split (the decoder in front passes over it inside a stored block) -- or never see it"""
+    filt, z = photo_stream(256, 128)
+    inner = zlib.compress(filt, 6)[2:-4]              # raw deflate: starts with a real dynamic header
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, 200_000, dtype=np.uint8).tobytes()
+    plain = filt + noise[:70_000] + inner + noise[70_000:] + filt
+    z2 = zlib.compress(plain, 6)
+    for nseg in (2, 3, 4):
+        rc, got, _ = run_segmented(seglib, z2, len(plain), nseg)
+        assert rc == 1 or got == plain

@@ -323,3 +323,63 @@ def test_inflate_large_gzip_and_zlib_streams(pngb200, ctx, orc):
         assert d.checksum == (zlib.crc32(ref) if fmts[i] == pngb200.FORMAT_GZIP else zlib.adler32(ref))
     ost, oout, ores = orc.inflate(streams[1])
     assert ost == 0 and got[1][2].blocks == ores.blocks and got[1][2].consumed_bits == ores.consumed_bits
+
+
+# ---- more than one CTA per stream (csrc/inflate_segments.cuh): few big streams are cut at block boundaries ----
+def test_segmented_decode_matches_whole_stream_decode(pngb200, ctx, orc):
+    """two 2048x1536 RGBA8 and one RGBA16 image (BASELINE config 4's per-GPU shape in small): cut into segments
+    by the automatic path, decoded whole with mode 2, compared with the source pixels and with each other"""
+    imgs = [corpus.make("photo", 2048, 1536, 21), corpus.make("photo", 2048, 1536, 22), corpus.make("photo", 1536, 1024, 23, True)]
+    jobs = []
+    for im, (bpp, depth) in zip(imgs, [(4, 8), (4, 8), (8, 16)]):
+        filt, z = corpus.zlib_png_stream(im, bpp, 6)
+        jobs.append(dict(idat=z, width=im.shape[1], height=im.shape[0], volume=8 * bpp, depth=depth, interlaced=0, fmt=0))
+    got = pngb200.decode_batch(ctx, jobs)
+    stats = ctx.segment_stats()
+    assert stats["streams"] == 3 and stats["segments"] > 6 and stats["fallbacks"] == 0, stats
+    ctx.set_inflate_mode(2)
+    try:
+        whole = pngb200.decode_batch(ctx, jobs)
+        assert ctx.segment_stats()["streams"] == 0
+    finally:
+        ctx.set_inflate_mode(0)
+    for g, w, im in zip(got, whole, imgs):
+        assert g.status == w.status == 0
+        assert g.pixels == w.pixels == np.ascontiguousarray(im).tobytes()
+        assert (g.checksum, g.produced, g.blocks) == (w.checksum, w.produced, w.blocks)
+
+
+def test_segmented_inflate_reference_streams_stored_blocks_and_lookalikes(pngb200, ctx, orc):
+    """streams as the reference's encoder writes them (few, growing blocks), stored + fixed blocks, and a complete
+    dynamic-block header hidden in stored data: whatever the split-point search finds, the bytes are zlib's"""
+    rng = np.random.default_rng(31)
+    filt, _ = corpus.zlib_png_stream(corpus.make("photo", 1024, 700, 24), 4, 6)
+    inner = zlib.compress(filt[:200_000], 6)[2:-4]
+    noise = rng.integers(0, 256, 1_500_000, dtype=np.uint8).tobytes()
+    cases = {
+        "reference level 9": (orc.deflate(filt, 9), filt),
+        "stored + lookalike": (zlib.compress(noise[:700_000] + inner + noise[700_000:] + filt, 6), noise[:700_000] + inner + noise[700_000:] + filt),
+        "fixed blocks": ((lambda c: c.compress(filt) + c.flush())(zlib.compressobj(6, zlib.DEFLATED, 15, 9, zlib.Z_FIXED)), filt),
+    }
+    streams = [v[0] for v in cases.values()]
+    got = pngb200.inflate_batch(ctx, streams, pngb200.FORMAT_ZLIB, caps=[len(v[1]) for v in cases.values()])
+    for (name, (z, plain)), (st, out, d) in zip(cases.items(), got):
+        ost, oout, ores = orc.inflate(z)
+        assert st == ost == 0, name
+        assert out == plain == oout, name
+        assert d.checksum == zlib.adler32(plain) and d.blocks == ores.blocks and d.consumed_bits == ores.consumed_bits, name
+
+
+def test_segmented_stream_errors_fall_back(pngb200, ctx, orc):
+    """a truncated and a corrupted big stream: the segments do not line up, the whole-stream path reports
+    exactly what the oracle reports"""
+    filt, z = corpus.zlib_png_stream(corpus.make("photo", 1600, 1200, 25), 4, 6)
+    bad = bytearray(z)
+    bad[len(z) // 2] ^= 0x10
+    streams = [z[: 2 * len(z) // 3], bytes(bad)]
+    got = pngb200.inflate_batch(ctx, streams, pngb200.FORMAT_ZLIB, caps=[len(filt)] * 2)
+    for s, (st, out, d) in zip(streams, got):
+        ost, oout, ores = orc.inflate(s, orc.ZLIB, len(filt))
+        assert st == ost, (st, ost)
+        if st == 0:
+            assert out == oout
