@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--inflate-mode", type=int, default=0)
     ap.add_argument("--mode", default="decode", choices=["decode", "encode", "inflate"],
                     help="inflate: BASELINE.json configs[4], standalone gzip streams of --sweep-mb sizes (device-resident)")
-    ap.add_argument("--sweep-mb", default="1,16,64", help="--mode inflate: uncompressed stream sizes in MiB")
+    ap.add_argument("--sweep-mb", default="1,16,256,1024", help="--mode inflate: uncompressed stream sizes in MiB")
     ap.add_argument("--encode-level", type=int, default=9)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: whole batch if <= 110 GB pinned)")
@@ -319,6 +319,30 @@ def main():
     value = world * B * npix * args.steps / (ms_max / 1e3) / 1e6
     stage /= args.steps
 
+    # ---------------- the 8-images-per-GPU row (BASELINE configs[3]'s per-GPU shape, SURVEY 8d "metric row"):
+    # fewer streams than CTA slots, so every stream is cut into segments (csrc/inflate_segments.cuh) ----------------
+    small = None
+    if B >= 8:
+        SB = 8
+        for _ in range(2):
+            ctx.check(L.pngb200_decode_batch_enqueue(ctx.handle, descs, SB, pkg.MEM_DEVICE))
+            ctx.check(L.pngb200_decode_batch_finish(ctx.handle, descs, SB))
+        seg = ctx.segment_stats()
+        assert all(descs[i].status == 0 and descs[i].checksum == items[i % len(items)]["adler"] for i in range(SB))
+        assert torch.equal(d_pixels[SB - 1], torch.frombuffer(bytearray(items[(SB - 1) % len(items)]["pixels"]), dtype=torch.uint8).cuda())
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(3):
+            ctx.check(L.pngb200_decode_batch_enqueue(ctx.handle, descs, SB, pkg.MEM_DEVICE))
+            ctx.check(L.pngb200_decode_batch_finish(ctx.handle, descs, SB))
+        s1.record(stream)
+        torch.cuda.synchronize()
+        sms = s0.elapsed_time(s1) / 3
+        small = {"images_per_gpu": SB, "value": SB * npix / (sms / 1e3) / 1e6, "unit": "MPixels/s (this GPU)", "ms_per_step": sms,
+                 "segments": seg["segments"], "segment_fallbacks": seg["fallbacks"], "stage_ms": dict(zip(("inflate", "checksum", "unfilter"), ctx.stage_ms())),
+                 "counters": ctx.inflate_counters(SB)}
+
     # ---------------- e2e: same call, HOST (pinned) buffers, copies inside the timed region ----------------
     e2e = None
     if not args.no_e2e:
@@ -390,6 +414,9 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * npix * esteps / float(dt.item()) / 1e6, "unit": "MPixels/s",
                "h2d_bytes_per_step": comp_total, "d2h_bytes_per_step": B * storage_bytes, "steps": esteps,
+               "pcie_ceiling": {"value": 44.7e9 / (storage_bytes / npix) / 1e6 * world, "unit": "MPixels/s",
+                                "note": "D2H of the decoded pixels at the 44.7 GB/s this box moves each way when both "
+                                        "directions run (profiles/r01_pcie_bandwidth.json)"},
                "images_per_gpu": B, "api": "pngb200_png_decode_batch" if args.e2e_api == "files" else "pngb200_decode_batch",
                "note": ("whole PNG files (65544-byte IDAT chunks) in pinned HOST memory: chunk walk on the host, "
                         "chunk CRC-32, IDAT gather, inflate and unfilter on the device; "
@@ -425,7 +452,8 @@ def main():
     comp_step = sum(len(items[i % len(items)]["idat"]) for i in range(B))
     alg_bytes = comp_step + B * storage_bytes  # C + P per image x images per launch
     dominant = int(np.argmax(stage))
-    names = ["inflate_parallel_kernel", "checksum kernels", "unfilter_wave_kernel"]
+    inflate_kernel = "inflate_wave_kernel" if B <= 296 else "inflate_parallel_kernel"  # pngb200_api.cu run_inflate
+    names = [inflate_kernel, "checksum kernels", "unfilter_wave_kernel"]
     achieved = alg_bytes / (stage[0] / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -445,15 +473,17 @@ def main():
         threads = os.cpu_count() or 1
         n_cpu = args.cpu_images or (threads if npix > 4_000_000 else 4 * threads)
         v, dt = cpu_decode_rate(items, w, h, bpp, depth, n_cpu, threads)
-        cpu = {"value": v, "unit": "MPixels/s", "cores": threads, "kind": "port",
-               "sample": f"{n_cpu} images of the same workload over {threads} host threads in {dt:.1f}s; "
-                         "C restatement of the Swift reference (oracle/), no Swift toolchain in the image"}
+        v1, dt1 = cpu_decode_rate(items, w, h, bpp, depth, 2 if npix > 4_000_000 else 8, 1)
+        cpu = {"value": v, "unit": "MPixels/s", "cores": threads, "kind": "port", "one_thread": v1,
+               "sample": f"{n_cpu} images of the same workload over {threads} host threads in {dt:.1f}s "
+                         f"(one thread alone: {v1:.1f} MPixels/s); C restatement of the Swift reference (oracle/, "
+                         "thread-local scratch), no Swift toolchain in the image"}
 
     line = {"metric": "MPixels/s decode (inflate+unfilter)", "value": value, "unit": "MPixels/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config, "clocks": clocks.summary(), "gpu_launches": int(launches),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "bit_exact": True,
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "bit_exact": True, "small_batch": small,
             "inflate_stats_per_step": stats}
     print(json.dumps(line))
     if world > 1:
@@ -462,8 +492,8 @@ def main():
 
 def main_inflate(args, rank, local_rank, world):
     """BASELINE.json configs[4]: standalone LZ77 / Gzip.Inflator throughput on gzip streams of S0 filtered
-    bytes, device-resident, one JSON line with a row per stream size.  One CTA
-    decodes one stream, so every size is run as min(592, ~6 GiB / size) independent streams."""
+    bytes, device-resident, one JSON line with two rows per stream size: ONE stream
+    (cut into segments, one CTA each: csrc/inflate_segments.cuh) and min(296, ~6 GiB / size) independent streams."""
     import zlib
 
     import numpy as np
@@ -482,34 +512,37 @@ def main_inflate(args, rank, local_rank, world):
         plain = (base * (n // len(base) + 1))[:n]
         co = zlib.compressobj(6, zlib.DEFLATED, 31)  # gzip wrapper
         z = co.compress(plain) + co.flush()
-        count = max(1, min(592, (6 << 30) // n))
+        crc = zlib.crc32(plain)
         d_src = torch.frombuffer(bytearray(z), dtype=torch.uint8).cuda()
-        d_in = [d_src.clone() for _ in range(count)]
-        d_out = torch.empty((count, n), dtype=torch.uint8, device="cuda")
-        descs = (pkg.StreamDesc * count)()
-        for i in range(count):
-            descs[i].src, descs[i].src_len = d_in[i].data_ptr(), len(z)
-            descs[i].dst, descs[i].dst_cap = d_out[i].data_ptr(), n
-            descs[i].format = pkg.FORMAT_GZIP
-        for _ in range(2):
-            ctx.check(L.pngb200_inflate_batch(ctx.handle, descs, count, pkg.MEM_DEVICE))
-        assert all(descs[i].status == 0 and descs[i].produced == n for i in range(count))
-        assert descs[0].checksum == zlib.crc32(plain) and bytes(d_out[count - 1].cpu().numpy().tobytes()) == plain
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        steps = max(1, args.steps)
-        for _ in range(steps):
-            ctx.check(L.pngb200_inflate_batch(ctx.handle, descs, count, pkg.MEM_DEVICE))
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        rows.append({"stream_mib": mb, "streams": count, "compressed_bytes": len(z), "ms_per_batch": ms,
-                     "out_GBps": count * n / ms / 1e6, "c_plus_u_GBps": count * (n + len(z)) / ms / 1e6,
-                     "per_stream_MBps": n / ms / 1e3})
-        del d_in, d_out, d_src
-        torch.cuda.empty_cache()
-        ctx.trim()
+        for count in sorted({1, max(1, min(296, (6 << 30) // n))}):
+            d_in = [d_src.clone() for _ in range(count)]
+            d_out = torch.empty((count, n), dtype=torch.uint8, device="cuda")
+            descs = (pkg.StreamDesc * count)()
+            for i in range(count):
+                descs[i].src, descs[i].src_len = d_in[i].data_ptr(), len(z)
+                descs[i].dst, descs[i].dst_cap = d_out[i].data_ptr(), n
+                descs[i].format = pkg.FORMAT_GZIP
+            for _ in range(2):
+                ctx.check(L.pngb200_inflate_batch(ctx.handle, descs, count, pkg.MEM_DEVICE))
+            seg = ctx.segment_stats()
+            assert all(descs[i].status == 0 and descs[i].produced == n for i in range(count))
+            assert descs[0].checksum == crc and bytes(d_out[count - 1].cpu().numpy().tobytes()) == plain
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            steps = max(1, args.steps)
+            for _ in range(steps):
+                ctx.check(L.pngb200_inflate_batch(ctx.handle, descs, count, pkg.MEM_DEVICE))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            rows.append({"stream_mib": mb, "streams": count, "compressed_bytes": len(z), "ms_per_batch": ms,
+                         "out_GBps": count * n / ms / 1e6, "c_plus_u_GBps": count * (n + len(z)) / ms / 1e6,
+                         "per_stream_MBps": n / ms / 1e3, "segments": seg["segments"], "segment_fallbacks": seg["fallbacks"]})
+            del d_in, d_out
+            torch.cuda.empty_cache()
+            ctx.trim()
+        del d_src
     if rank == 0:
         best = max(r["c_plus_u_GBps"] for r in rows)
         print(json.dumps({"metric": "GB/s standalone gzip inflate (C+U)", "value": best, "unit": "GB/s", "n_gpus": world,

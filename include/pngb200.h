@@ -362,6 +362,25 @@ size_t pngb200_inflator_pull_all(pngb200_inflator* z, uint8_t* dst, size_t cap);
 size_t pngb200_inflator_available(const pngb200_inflator* z);
 void   pngb200_inflator_error(const pngb200_inflator* z, int* status, uint32_t* a, uint32_t* b);
 
+/* LZ77.Deflator value-type semantics (Sources/LZ77/Deflator/LZ77.Deflator.swift:8-44; the call sites are
+ * PNG.Encoder.pull, Sources/PNG/Encoding/PNG.Encoder.swift:68,85,101,117,121,128).
+ * init(format:level:exponent:hint:) -- `chunk_bytes` is the size of a complete output block: the reference hands out
+ * 2 * capacity bytes, capacity being whatever malloc grants for `hint` UInt16 atoms (LZ77.DeflatorOut.swift:15-27,
+ * 109-135); 0 = 65544, the value behind the reference's committed outputs (hint 1 << 15).
+ * The device compresses a stream in one launch, so compressed blocks become available when push(last:) arrives;
+ * pop() before that returns "nil" where the reference might already have a block.  The sequence of blocks a
+ * caller sees -- sizes and bytes -- is the reference's. */
+typedef struct pngb200_deflator pngb200_deflator;
+pngb200_deflator* pngb200_deflator_create(pngb200_ctx* ctx, int format, int level, int exponent, size_t chunk_bytes);
+void              pngb200_deflator_destroy(pngb200_deflator* z);
+/* push(_:last:) : copies `data`.  Returns PNGB200_OK, or < 0 when compressing (on last) failed */
+int    pngb200_deflator_push(pngb200_deflator* z, const uint8_t* data, size_t n, int last);
+/* pop() : a complete block (exactly chunk_bytes) -> returns 1 and sets *block / *n (valid until the next call on
+ * this handle); 0 = nil */
+int    pngb200_deflator_pop(pngb200_deflator* z, const uint8_t** block, size_t* n);
+/* pull() : a complete block if there is one, else the flushed incomplete block (non-empty); 0 = nil */
+int    pngb200_deflator_pull(pngb200_deflator* z, const uint8_t** block, size_t* n);
+
 #ifdef __cplusplus
 }
 #endif

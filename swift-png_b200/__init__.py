@@ -223,6 +223,15 @@ def lib():
     L.pngb200_ctx_stage_ms.restype = C.c_int
     L.pngb200_ctx_inflate_stats.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_inflate_stats.restype = C.c_int
+    L.pngb200_deflator_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t]
+    L.pngb200_deflator_create.restype = C.c_void_p
+    L.pngb200_deflator_destroy.argtypes = [C.c_void_p]
+    L.pngb200_deflator_destroy.restype = None
+    L.pngb200_deflator_push.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int]
+    L.pngb200_deflator_push.restype = C.c_int
+    for fn in (L.pngb200_deflator_pop, L.pngb200_deflator_pull):
+        fn.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
+        fn.restype = C.c_int
     L.pngb200_ctx_segment_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_segment_stats.restype = C.c_int
     L.pngb200_ctx_inflate_counters.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
@@ -659,6 +668,42 @@ def encode_batch(ctx: Context, images, level: int = 9):
         descs[i].level = g.get("level", level)
     ctx.check(ctx._lib.pngb200_encode_batch(ctx.handle, descs, n, MEM_HOST))
     return [(descs[i].status, keep[i][1].raw[: descs[i].produced]) for i in range(n)]
+
+
+class Deflator:
+    """LZ77.Deflator value semantics (push(_:last:), pop(), pull()) over the GPU encoder."""
+
+    def __init__(self, ctx: Context, fmt: int = FORMAT_ZLIB, level: int = 9, exponent: int = 15, chunk_bytes: int = 0):
+        self.ctx = ctx
+        L = ctx._lib
+        self.handle = L.pngb200_deflator_create(ctx.handle, fmt, level, exponent, chunk_bytes)
+        if not self.handle:
+            raise PNGB200Error(ERR_BAD_ARGUMENT, "deflator_create")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx._lib.pngb200_deflator_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def push(self, data: bytes, last: bool = False):
+        self.ctx.check(self.ctx._lib.pngb200_deflator_push(self.handle, bytes(data), len(data), int(last)))
+
+    def _take(self, fn):
+        p, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        got = fn(self.handle, C.byref(p), C.byref(n))
+        if got < 0:
+            raise PNGB200Error(got, "deflator")
+        return C.string_at(p, n.value) if got else None
+
+    def pop(self):
+        """a complete block or None (Swift: pop() -> [UInt8]?)"""
+        return self._take(self.ctx._lib.pngb200_deflator_pop)
+
+    def pull(self):
+        """a complete block, else the flushed rest, else None (Swift: pull() -> [UInt8]?)"""
+        return self._take(self.ctx._lib.pngb200_deflator_pull)
 
 
 class Inflator:

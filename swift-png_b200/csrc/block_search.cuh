@@ -14,14 +14,28 @@
 
 namespace pngb200 {
 
-__device__ __forceinline__ uint32_t bs_bits(const uint8_t* in, uint64_t nbytes, uint64_t bit, int count)
+// 57 or more bits of the stream starting at bit `bit` (zero beyond the end): three aligned words when they lie
+// inside the buffer, bytes at its edges
+__device__ __forceinline__ uint64_t bs_bits64(const uint8_t* in, uint64_t nbytes, uint64_t bit)
 {
+    const uint64_t  byte = bit >> 3;
+    const uintptr_t a = (uintptr_t)in + byte, a4 = a & ~(uintptr_t)3;
+    if (a4 >= (uintptr_t)in && a4 + 12 <= (uintptr_t)in + nbytes) {
+        const uint32_t* w = (const uint32_t*)a4;
+        const uint32_t  w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+        const uint32_t  sh = (uint32_t)(a & 3) * 8 + (uint32_t)(bit & 7);   // < 32
+        const uint32_t  lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        return (uint64_t)hi << 32 | lo;
+    }
     uint64_t v = 0;
-    const uint64_t byte = bit >> 3;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         if (byte + k < nbytes) v |= (uint64_t)in[byte + k] << (8 * k);
-    return (uint32_t)((v >> (bit & 7)) & ((1ull << count) - 1));
+    return v >> (bit & 7);
+}
+__device__ __forceinline__ uint32_t bs_bits(const uint8_t* in, uint64_t nbytes, uint64_t bit, int count)
+{
+    return (uint32_t)(bs_bits64(in, nbytes, bit) & ((1ull << count) - 1));
 }
 
 // 0 = plausible dynamic-block header at bit p; otherwise the stage that rejected it (as in block_probe.c)
@@ -29,8 +43,9 @@ __device__ int bs_probe_dynamic_header(const uint8_t* in, uint64_t n, uint64_t p
 {
     const uint64_t total = n * 8;
     if (p + 17 > total) return 7;
-    if (bs_bits(in, n, p + 1, 2) != 2) return 1;
-    const uint32_t hlit = bs_bits(in, n, p + 3, 5), hdist = bs_bits(in, n, p + 8, 5), hclen = bs_bits(in, n, p + 13, 4);
+    const uint64_t head = bs_bits64(in, n, p);                    // BFINAL, BTYPE, HLIT, HDIST, HCLEN: 17 bits
+    if (((head >> 1) & 3) != 2) return 1;
+    const uint32_t hlit = (uint32_t)(head >> 3) & 31, hdist = (uint32_t)(head >> 8) & 31, hclen = (uint32_t)(head >> 13) & 15;
     if (hlit > 29 || hdist > 29) return 2;
     uint64_t at = p + 17;
     if (at + 3 * (uint64_t)(hclen + 4) > total) return 7;
@@ -39,10 +54,14 @@ __device__ int bs_probe_dynamic_header(const uint8_t* in, uint64_t n, uint64_t p
 #pragma unroll
     for (int i = 0; i < 19; ++i) cl[i] = 0;
     uint32_t kraft = 0;
-    for (uint32_t i = 0; i < hclen + 4; ++i, at += 3) {
-        const uint32_t l = bs_bits(in, n, at, 3);
-        cl[order[i]] = (uint8_t)l;
-        if (l) kraft += 128u >> l;
+    {
+        const uint64_t v = bs_bits64(in, n, at);                  // up to 19 x 3 = 57 bits in one fetch
+        for (uint32_t i = 0; i < hclen + 4; ++i) {
+            const uint32_t l = (uint32_t)(v >> (3 * i)) & 7;
+            cl[order[i]] = (uint8_t)l;
+            if (l) kraft += 128u >> l;
+        }
+        at += 3 * (uint64_t)(hclen + 4);
     }
     if (kraft != 128) return 3;
     uint32_t count[8], first[8], offs[8];
@@ -113,22 +132,24 @@ struct SearchJob {
     uint64_t       found;    // out: first plausible offset, or ~0 if none before limit_bit
 };
 
-// one CTA per job; CTA-width offsets per step, minimum over the CTA, stop at the first step with a hit
+// BS_CTAS CTAs per job (blockIdx.y), each testing every BS_CTAS-th chunk of 256 consecutive offsets; the
+// smallest hit wins (atomicMin on job.found, which the host presets to ~0) and a CTA stops as soon as its next
+// chunk lies behind the best hit so far
+constexpr uint32_t BS_CTAS = 8;
 __global__ void __launch_bounds__(256) block_search_kernel(SearchJob* jobs, uint32_t count)
 {
     if (blockIdx.x >= count) return;
     SearchJob& job = jobs[blockIdx.x];
+    unsigned long long* const found = reinterpret_cast<unsigned long long*>(&job.found);
     __shared__ unsigned long long best;
-    if (threadIdx.x == 0) best = ~0ull;
-    __syncthreads();
-    for (uint64_t base = job.from_bit; base < job.limit_bit; base += blockDim.x) {
-        const uint64_t p = base + threadIdx.x;
-        if (p < job.limit_bit && bs_probe_dynamic_header(job.src, job.src_len, p) == 0) atomicMin(&best, (unsigned long long)p);
+    for (uint64_t base = job.from_bit + (uint64_t)blockIdx.y * blockDim.x; base < job.limit_bit; base += (uint64_t)gridDim.y * blockDim.x) {
+        if (threadIdx.x == 0) best = *reinterpret_cast<volatile unsigned long long*>(found);
         __syncthreads();
-        if (best != ~0ull) break;
+        if (best < base) break;
+        const uint64_t p = base + threadIdx.x;
+        if (p < job.limit_bit && bs_probe_dynamic_header(job.src, job.src_len, p) == 0) atomicMin(found, (unsigned long long)p);
         __syncthreads();
     }
-    if (threadIdx.x == 0) job.found = best;
 }
 
 }  // namespace pngb200

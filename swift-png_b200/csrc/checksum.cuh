@@ -10,12 +10,14 @@
 #pragma once
 
 #include "common.cuh"
+#include "crc32.cuh"
 
 namespace pngb200 {
 
 constexpr uint32_t CK_CHUNK   = 1u << 16;
 constexpr uint32_t CK_THREADS = 256;
 constexpr uint32_t ADLER_MOD  = 65521;
+static_assert(CK_CHUNK == CRC_PIECE && CK_THREADS == CRC_THREADS, "the gzip branch reuses crc_piece_cta");
 
 struct ChecksumParams {
     const StreamJob* jobs;
@@ -24,6 +26,7 @@ struct ChecksumParams {
     uint64_t*        partial;     // [total_chunks][2]: sum b, sum (L - k) b  (or crc, length)
     uint32_t         count;
     uint32_t         total_chunks;
+    const uint32_t*  crc_tables;  // CRC_TABLE_WORDS (crc32.cuh); needed when the batch holds gzip streams
 };
 
 __device__ __forceinline__ uint32_t crc32_byte_table(uint32_t i)
@@ -53,12 +56,18 @@ __global__ void __launch_bounds__(CK_THREADS) checksum_chunk_kernel(ChecksumPara
     const uint32_t L = off < n ? (uint32_t)min((uint64_t)CK_CHUNK, n - off) : 0;
     const uint8_t* src = job.dst + off;
     if (job.format == PNGB200_FORMAT_GZIP) {
-        // CRC-32 of the chunk: bytewise by thread 0 of the chunk (gzip streams are the
-        // secondary path; the fold below combines chunk CRCs with the GF(2) shift operator)
+        // CRC-32 of the chunk by the whole CTA (256-byte slices combined with GF(2) shift operators, the
+        // same device code as crc_regions_kernel); the fold below combines the chunk CRCs
+        __shared__ uint32_t table[256];
+        __shared__ uint32_t ops[16 * 32];
+        __shared__ uint32_t cred[CRC_THREADS / 32];
+        table[threadIdx.x] = p.crc_tables[threadIdx.x];
+        ops[threadIdx.x] = p.crc_tables[256 + threadIdx.x];
+        ops[threadIdx.x + 256] = p.crc_tables[512 + threadIdx.x];
+        __syncthreads();
+        const uint32_t crc = crc_piece_cta(src, L, table, ops, cred);
         if (threadIdx.x == 0) {
-            uint32_t crc = 0xffffffffu;
-            for (uint32_t k = 0; k < L; ++k) crc = crc32_byte_table((crc ^ src[k]) & 0xff) ^ (crc >> 8);
-            p.partial[2 * (uint64_t)chunk]     = ~crc;
+            p.partial[2 * (uint64_t)chunk]     = crc;
             p.partial[2 * (uint64_t)chunk + 1] = L;
         }
         return;

@@ -78,6 +78,40 @@ __device__ __forceinline__ uint32_t crc_shift(const uint32_t* ops, uint32_t crc,
     return crc;
 }
 
+// CRC-32 of `L` <= CRC_PIECE bytes at `ptr`, computed by a whole CTA of CRC_THREADS threads; valid on
+// thread 0.  `table` (256 words) and `ops` (16 x 32 words: shift operators for 2^0 .. 2^15 bytes) live in
+// shared memory, `red` is CRC_THREADS / 32 words of shared scratch.
+__device__ __forceinline__ uint32_t crc_piece_cta(const uint8_t* ptr, uint32_t L, const uint32_t* table,
+                                                  const uint32_t* ops, uint32_t* red)
+{
+    const uint32_t begin = min(L, threadIdx.x * CRC_SLICE), end = min(L, begin + CRC_SLICE);
+    uint32_t crc = 0;
+    if (end > begin) {
+        const uint8_t* s = ptr + begin;
+        uint32_t n = end - begin, c = 0xffffffffu;
+        while (n && (((uintptr_t)s) & 15)) { c = table[(c ^ *s++) & 0xff] ^ (c >> 8); --n; }
+        for (; n >= 16; n -= 16, s += 16) {
+            const uint4 v = *(const uint4*)s;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                c ^= w[q];  // slicing by one over a word: four dependent look-ups
+#pragma unroll
+                for (int b = 0; b < 4; ++b) c = table[c & 0xff] ^ (c >> 8);
+            }
+        }
+        while (n) { c = table[(c ^ *s++) & 0xff] ^ (c >> 8); --n; }
+        crc = crc_shift(ops, ~c, L - end);  // bytes of this piece that follow the slice
+    }
+    for (int o = 16; o; o >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = crc;
+    __syncthreads();
+    crc = 0;
+    if (threadIdx.x == 0)
+        for (uint32_t w = 0; w < CRC_THREADS / 32; ++w) crc ^= red[w];
+    return crc;
+}
+
 __global__ void __launch_bounds__(CRC_THREADS) crc_regions_kernel(CrcParams p)
 {
     __shared__ uint32_t table[256];
@@ -98,31 +132,8 @@ __global__ void __launch_bounds__(CRC_THREADS) crc_regions_kernel(CrcParams p)
     const uint64_t  off = (uint64_t)(piece - p.piece_base[lo]) * CRC_PIECE;
     const uint32_t  L   = off < reg.len ? (uint32_t)min((uint64_t)CRC_PIECE, reg.len - off) : 0;
     __syncthreads();
-    const uint32_t begin = min(L, threadIdx.x * CRC_SLICE), end = min(L, begin + CRC_SLICE);
-    uint32_t crc = 0;
-    if (end > begin) {
-        const uint8_t* s = reg.ptr + off + begin;
-        uint32_t n = end - begin, c = 0xffffffffu;
-        while (n && (((uintptr_t)s) & 15)) { c = table[(c ^ *s++) & 0xff] ^ (c >> 8); --n; }
-        for (; n >= 16; n -= 16, s += 16) {
-            const uint4 v = *(const uint4*)s;
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                c ^= w[q];  // slicing by one over a word: four dependent look-ups
-#pragma unroll
-                for (int b = 0; b < 4; ++b) c = table[c & 0xff] ^ (c >> 8);
-            }
-        }
-        while (n) { c = table[(c ^ *s++) & 0xff] ^ (c >> 8); --n; }
-        crc = crc_shift(ops, ~c, L - end);  // bytes of this piece that follow the slice
-    }
-    for (int o = 16; o; o >>= 1) crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = crc;
-    __syncthreads();
+    uint32_t crc = crc_piece_cta(reg.ptr + off, L, table, ops, red);
     if (threadIdx.x == 0) {
-        crc = 0;
-        for (uint32_t w = 0; w < CRC_THREADS / 32; ++w) crc ^= red[w];
         const uint32_t* all = p.tables + 256;
         crc = crc_shift(all, crc, reg.len - off - L);  // the rest of the region
         if (off == 0 && reg.has_prefix) {

@@ -1002,7 +1002,7 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     uint8_t* const  wdst   = dst + out * esz;     // HBM address of wave offset 0
                     const bool      in_hbm = sym || total > WV_OUT_BYTES;
                     const uint32_t  rbase  = (uint32_t)(out + mis) & 0xffffu;  // ring position of wave offset 0
-                    uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
+                    uint32_t* const U      = total > WV_OUT_BYTES ? gbitmap : sh.bitmap;   // (a segment's wave may fit the shared-memory bitmap)
                     if (!in_hbm && ring_stale) {
                         // the window [out - 32768, out) was written to HBM behind the ring's back: fetch it
                         const uint64_t lo = out > WV_WINDOW ? out - WV_WINDOW : 0;

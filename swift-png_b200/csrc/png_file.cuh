@@ -127,6 +127,14 @@ void walk_file(pngb200_png_desc& d, FileWalk& w)
         if (h[12] > 1) return stop(PNGB200_ERR_PARSE_HEADER_INTERLACING_CODE, h[12], 0, false);
         d.width = load_be32(h), d.height = load_be32(h + 4);
         if (!d.width || !d.height) return stop(PNGB200_ERR_PARSE_HEADER_SIZE, d.width, d.height, false);
+        {
+            // the reference traps when the storage size overflows (PNG.Image.swift:84); refuse such a file here
+            const uint64_t bpp = (uint64_t)((depth * channels_of_color(color) + 7) >> 3);
+            uint64_t prod;
+            if (d.width > 0x7fffffffu || d.height > 0x7fffffffu ||
+                __builtin_mul_overflow((uint64_t)d.width * d.height, bpp ? bpp : 1, &prod) || prod > (1ull << 46))
+                return stop(PNGB200_ERR_PARSE_HEADER_SIZE, d.width, d.height, false);
+        }
         d.depth = (uint8_t)depth, d.color = (uint8_t)color, d.interlaced = h[12];
         d.format.color = d.color, d.format.depth = d.depth, d.format.bgr = d.standard;
         d.storage_size = (uint64_t)d.width * d.height * (uint64_t)((depth * channels_of_color(color) + 7) >> 3);
@@ -207,17 +215,6 @@ void walk_file(pngb200_png_desc& d, FileWalk& w)
         }
         if (!lex()) return;
     }
-}
-
-int ensure_crc_tables(pngb200_ctx* ctx)
-{
-    if (ctx->d_crctab.p) return PNGB200_OK;
-    std::vector<uint32_t> t(CRC_TABLE_WORDS);
-    crc_build_tables(t.data());
-    CU(ctx->d_crctab.reserve(sizeof(uint32_t) * CRC_TABLE_WORDS));
-    CU(cudaMemcpyAsync(ctx->d_crctab.p, t.data(), sizeof(uint32_t) * CRC_TABLE_WORDS, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return PNGB200_OK;
 }
 
 // CRC-32 of `regions` (device pointers) in three enqueue steps, so that a caller can put the small

@@ -157,6 +157,18 @@ struct DeviceGuard {
     }
 };
 
+// the CRC-32 byte table and shift operators (crc32.cuh), uploaded once per context
+int ensure_crc_tables(pngb200_ctx* ctx)
+{
+    if (ctx->d_crctab.p) return PNGB200_OK;
+    std::vector<uint32_t> t(CRC_TABLE_WORDS);
+    crc_build_tables(t.data());
+    CU(ctx->d_crctab.reserve(sizeof(uint32_t) * CRC_TABLE_WORDS));
+    CU(cudaMemcpyAsync(ctx->d_crctab.p, t.data(), sizeof(uint32_t) * CRC_TABLE_WORDS, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PNGB200_OK;
+}
+
 // ---- more than one CTA per stream (inflate_segments.cuh) ----
 // Streams of `par` that are worth cutting are decoded here, segment by segment; on return `par` holds the
 // streams that still have to go through the whole-stream kernels (not cut, or a segment did not line up).
@@ -174,7 +186,7 @@ int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t
     size_t nsearch = 0;
     for (uint32_t i : par) {
         const size_t nseg = std::min<size_t>(per_stream, h_jobs[i].src_len / kMinSegment);
-        if (nseg < 2 || h_jobs[i].start_bit != 0 || h_jobs[i].phase != 0 || h_jobs[i].dst_cap < (1u << 20)) continue;
+        if (nseg < 4 || h_jobs[i].start_bit != 0 || h_jobs[i].phase != 0 || h_jobs[i].dst_cap < (1u << 20)) continue;
         cuts.push_back(Cut{i, (uint32_t)nseg, nsearch});
         nsearch += nseg - 1;
     }
@@ -196,7 +208,7 @@ int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t
         }
     }
     CU(cudaMemcpyAsync(ctx->d_sgsearch.p, sj, sizeof(SearchJob) * nsearch, cudaMemcpyHostToDevice, ctx->stream));
-    block_search_kernel<<<(unsigned)nsearch, 256, 0, ctx->stream>>>(ctx->d_sgsearch.as<SearchJob>(), (uint32_t)nsearch);
+    block_search_kernel<<<dim3((unsigned)nsearch, BS_CTAS), 256, 0, ctx->stream>>>(ctx->d_sgsearch.as<SearchJob>(), (uint32_t)nsearch);
     ctx->launches++;
     CU(cudaMemcpyAsync(sj, ctx->d_sgsearch.p, sizeof(SearchJob) * nsearch, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -305,7 +317,15 @@ int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t
         f.resume_out = total;
         f.ck_done = 0;
         f.stat_waves = 0;
-        for (uint32_t k = lo; k < hi; ++k) f.stat_waves += sr[k].stat_waves;
+        f.stat_tokens = f.stat_matches = f.stat_deferred = 0;
+        for (int q = 0; q < 12; ++q) f.stat_cycles[q] = 0;
+        for (uint32_t k = lo; k < hi; ++k) {
+            f.stat_waves += sr[k].stat_waves;
+            f.stat_tokens += sr[k].stat_tokens;
+            f.stat_matches += sr[k].stat_matches;
+            f.stat_deferred += sr[k].stat_deferred;
+            for (int q = 0; q < 12; ++q) f.stat_cycles[q] += sr[k].stat_cycles[q];
+        }
         finals.push_back(f);
     }
     if (!recs.empty()) {
@@ -483,6 +503,13 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
     cp.partial = ctx->d_partial.as<uint64_t>();
     cp.count = (uint32_t)count;
     cp.total_chunks = (uint32_t)total;
+    cp.crc_tables = nullptr;
+    for (size_t i = 0; i < count; ++i)
+        if (h_jobs[i].format == PNGB200_FORMAT_GZIP) {
+            if (int rc = ensure_crc_tables(ctx)) return rc;
+            cp.crc_tables = ctx->d_crctab.as<uint32_t>();
+            break;
+        }
     if (total) {
         checksum_chunk_kernel<<<(unsigned)total, CK_THREADS, 0, ctx->stream>>>(cp);
         ctx->launches++;
@@ -505,6 +532,16 @@ struct Geometry {
 bool geometry(uint32_t w, uint32_t h, int volume, int depth, int interlaced, Geometry* g)
 {
     if (w == 0 || h == 0 || volume <= 0 || volume > 64 || depth <= 0 || depth > 16) return false;
+    // Dimensions come from untrusted files: the reference traps when w * h * bpp overflows (PNG.Image.swift:84);
+    // here an image whose sizes do not fit is refused before any buffer is sized from a wrapped product.
+    {
+        if (w > 0x7fffffffu || h > 0x7fffffffu) return false;
+        const uint64_t pitch64 = ((uint64_t)w * (uint64_t)volume + 7) >> 3;
+        uint64_t prod;
+        if (pitch64 > 0xfffffff0ull) return false;
+        if (__builtin_mul_overflow((uint64_t)h, pitch64 + 1, &prod) || prod > (1ull << 46)) return false;
+        if (__builtin_mul_overflow((uint64_t)w * (uint64_t)h, (uint64_t)((volume + 7) >> 3), &prod) || prod > (1ull << 46)) return false;
+    }
     g->filtered = pngb200_filtered_size(w, h, volume, interlaced);
     g->storage  = pngb200_storage_size(w, h, volume);
     g->pitch    = (uint32_t)(((uint64_t)w * volume + 7) >> 3);
@@ -618,9 +655,9 @@ int run_over_lanes(pngb200_ctx* ctx, size_t count, int memspace, BytesOf bytes_o
 {
     size_t bytes = 0;
     for (size_t i = 0; i < count; ++i) bytes += bytes_of(i);
-    // tunable for experiments: PNGB200_LANES, PNGB200_CHUNKS_PER_LANE (0 / unset = the rule above)
-    const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 4;
-    const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(0, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 0;
+    // tunable for experiments: PNGB200_LANES, PNGB200_CHUNKS_PER_LANE (0 / unset = the rule above); read once
+    static const size_t kLanes = getenv("PNGB200_LANES") ? std::max(1, atoi(getenv("PNGB200_LANES"))) : 4;
+    static const size_t kPerLane = getenv("PNGB200_CHUNKS_PER_LANE") ? std::max(0, atoi(getenv("PNGB200_CHUNKS_PER_LANE"))) : 0;
     constexpr size_t kMinChunk = 32;
     if (memspace != PNGB200_MEM_HOST || count < 2 * kMinChunk || bytes < ((size_t)256 << 20)) return work(ctx, 0, count);
     while (ctx->lanes.size() < kLanes) {
@@ -652,16 +689,20 @@ int run_over_lanes(pngb200_ctx* ctx, size_t count, int memspace, BytesOf bytes_o
         workers.emplace_back([&, l]() {
             pngb200_ctx* lane = ctx->lanes[l];
             lane->inflate_mode = ctx->inflate_mode;
+            lane->parallel_threshold = ctx->parallel_threshold;
             for (size_t c = l; c < nchunks; c += kLanes) {
                 size_t lo = cut[c], n = cut[c + 1] - cut[c];
                 if (n == 0) continue;
                 int rc = work(lane, lo, n);
-                if (rc != PNGB200_OK) { rcs[l] = rc; ctx->error = lane->error; return; }
+                if (rc != PNGB200_OK) { rcs[l] = rc; return; }   // the lane keeps its own error text
             }
         });
     for (std::thread& t : workers) t.join();
-    for (int rc : rcs)
-        if (rc != PNGB200_OK) return rc;
+    for (size_t l = 0; l < kLanes; ++l)
+        if (rcs[l] != PNGB200_OK) {
+            ctx->error = ctx->lanes[l]->error;   // after the join: one writer
+            return rcs[l];
+        }
     return PNGB200_OK;
 }
 }  // namespace
@@ -1164,6 +1205,84 @@ int pngb200_filter_batch(pngb200_ctx* ctx, pngb200_filter_desc* im, size_t count
 
 }  // extern "C"
 
+// ---------------- streaming LZ77.Deflator handle ----------------
+struct pngb200_deflator {
+    pngb200_ctx*         ctx = nullptr;
+    int                  format = 0, level = 9, exponent = 15;
+    size_t               chunk = 65544;
+    std::vector<uint8_t> input, output;
+    size_t               at = 0;       // next output byte to hand out
+    bool                 finished = false;
+};
+
+extern "C" {
+
+pngb200_deflator* pngb200_deflator_create(pngb200_ctx* ctx, int format, int level, int exponent, size_t chunk_bytes)
+{
+    if (!ctx || format < 0 || format > 2 || level < 0 || level > 13 || exponent < 8 || exponent > 15) {
+        set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "deflator_create: bad format / level / exponent");
+        return nullptr;
+    }
+    pngb200_deflator* z = new pngb200_deflator();
+    z->ctx = ctx;
+    z->format = format;
+    z->level = level;
+    z->exponent = exponent;
+    z->chunk = chunk_bytes ? chunk_bytes : 65544;
+    return z;
+}
+
+void pngb200_deflator_destroy(pngb200_deflator* z) { delete z; }
+
+int pngb200_deflator_push(pngb200_deflator* z, const uint8_t* data, size_t n, int last)
+{
+    if (!z || (!data && n)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (z->finished) return set_error(z->ctx, PNGB200_ERR_BAD_ARGUMENT, "deflator: push after push(last: true)");
+    z->input.insert(z->input.end(), data, data + n);
+    if (!last) return PNGB200_OK;
+    z->output.resize(pngb200_deflate_bound(z->input.size()));
+    pngb200_deflate_desc d;
+    memset(&d, 0, sizeof d);
+    d.src = z->input.data();
+    d.src_len = z->input.size();
+    d.dst = z->output.data();
+    d.dst_cap = z->output.size();
+    d.format = z->format;
+    d.level = z->level;
+    d.exponent = z->exponent;
+    int rc = pngb200_deflate_batch(z->ctx, &d, 1, PNGB200_MEM_HOST);
+    if (rc != PNGB200_OK) return rc;
+    if (d.status != PNGB200_OK) return d.status;
+    z->output.resize((size_t)d.produced);
+    z->finished = true;
+    std::vector<uint8_t>().swap(z->input);
+    return PNGB200_OK;
+}
+
+int pngb200_deflator_pop(pngb200_deflator* z, const uint8_t** block, size_t* n)
+{
+    if (!z || !block || !n) return PNGB200_ERR_BAD_ARGUMENT;
+    // DeflatorOut queues a block the moment its buffer is full (LZ77.DeflatorOut.swift:109-135): complete blocks only
+    if (!z->finished || z->output.size() - z->at < z->chunk) return 0;
+    *block = z->output.data() + z->at;
+    *n = z->chunk;
+    z->at += z->chunk;
+    return 1;
+}
+
+int pngb200_deflator_pull(pngb200_deflator* z, const uint8_t** block, size_t* n)
+{
+    if (!z || !block || !n) return PNGB200_ERR_BAD_ARGUMENT;
+    if (int got = pngb200_deflator_pop(z, block, n)) return got;
+    if (!z->finished || z->at >= z->output.size()) return 0;   // pull(): flushed.isEmpty ? nil : flushed
+    *block = z->output.data() + z->at;
+    *n = z->output.size() - z->at;
+    z->at = z->output.size();
+    return 1;
+}
+
+}  // extern "C"
+
 // ---------------- colour targets: unpack / pack ----------------
 namespace {
 int run_color(pngb200_ctx* ctx, pngb200_color_desc* im, size_t count, int target, int alpha_mode, int memspace, bool unpack)
@@ -1368,7 +1487,11 @@ extern "C" int pngb200_deflate_batch(pngb200_ctx* ctx, pngb200_deflate_desc* s, 
 extern "C" int pngb200_encode_batch(pngb200_ctx* ctx, pngb200_encode_desc* im, size_t count, int memspace)
 {
     if (!ctx || (!im && count)) return PNGB200_ERR_BAD_ARGUMENT;
+    if (ctx->pending) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "a decode batch is pending");
     if (count == 0) return PNGB200_OK;
+    for (size_t i = 0; i < count; ++i)
+        if (!im[i].pixels || !im[i].idat)
+            return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "image %zu: bad descriptor", i);
     DeviceGuard guard(ctx->device);
     const bool host = memspace == PNGB200_MEM_HOST;
     // stage 1: filter into a private device workspace (device memspace of the filter entry point)
@@ -1530,6 +1653,11 @@ int pngb200_inflator_push(pngb200_inflator* z, const uint8_t* data, size_t n)
         cp.partial = z->d_partial.as<uint64_t>();
         cp.count = 1;
         cp.total_chunks = base[1];
+        cp.crc_tables = nullptr;
+        if (z->format == PNGB200_FORMAT_GZIP) {
+            if (int rc = ensure_crc_tables(ctx)) return rc;
+            cp.crc_tables = ctx->d_crctab.as<uint32_t>();
+        }
         checksum_chunk_kernel<<<base[1], CK_THREADS, 0, ctx->stream>>>(cp);
         checksum_fold_kernel<<<1, 32, 0, ctx->stream>>>(cp);
         ctx->launches += 2;

@@ -143,6 +143,12 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
     uint8_t*       out   = job.pixels + (uint64_t)(active ? y : 0) * pitch;
     const uint8_t* above = band == 0 ? nullptr : job.pixels + (uint64_t)(band * 32 - 1) * pitch;
     const bool     publish = lane == 31 && prog_mine != nullptr;
+    // rows the stream did not deliver (a complete zlib stream that is shorter than the image is not an error in
+    // the reference: the rows simply stay as PNG.Image.storage was initialised, zero -- PNG.Image.swift:84)
+    if (!active && y < job.height) {
+        uint8_t* z = job.pixels + (uint64_t)y * pitch;
+        for (uint32_t k = 0; k < pitch; ++k) z[k] = 0;
+    }
 
     uint4    qcur  = make_uint4(0, 0, 0, 0);
     uint4    mine  = make_uint4(0, 0, 0, 0);  // my last reconstructed chunk
@@ -294,6 +300,12 @@ __global__ void __launch_bounds__(128) unfilter_generic_kernel(const GenericJob*
     const int        tid = threadIdx.x, nt = blockDim.x;
     const uint32_t   bpp = job.bpp;
     uint8_t*         at  = job.filtered;
+    // PNG.Image.storage starts out zeroed (PNG.Image.swift:84): pixels no row reaches stay zero
+    {
+        const uint64_t total = (uint64_t)job.width * job.height * bpp;
+        for (uint64_t k = tid; k < total; k += nt) job.pixels[k] = 0;
+        __syncthreads();
+    }
     const uint8_t*   end = job.filtered + usable_bytes(job.inflated, job.filtered_len);
     const int npass = job.interlaced ? 7 : 1;
     for (int z = 0; z < npass; ++z) {

@@ -16,7 +16,7 @@ extern "C" int emu_inflate_segmented(const uint8_t* src, uint64_t len, uint8_t* 
     const uint64_t bits = 8 * len, step = bits / nseg;
     std::vector<SearchJob> sj;
     for (uint32_t k = 1; k < nseg; ++k) sj.push_back(SearchJob{src, len, k * step, k + 1 < nseg ? (k + 1) * step : bits, ~0ull});
-    if (!sj.empty()) simt::launch((unsigned)sj.size(), 256, 0, [&]() { block_search_kernel(sj.data(), (uint32_t)sj.size()); });
+    if (!sj.empty()) simt::launch((unsigned)sj.size(), 256, 0, [&]() { block_search_kernel(sj.data(), (uint32_t)sj.size()); }, 0, false, 256 << 10, BS_CTAS);
     std::vector<uint64_t> at{0};
     for (auto& q : sj)
         if (q.found != ~0ull) at.push_back(q.found);

@@ -124,8 +124,11 @@ inline void fiber_entry()
 // order: 0 ascending, 1 descending, >= 2 pseudo-random with that seed
 // interleave: all CTAs resident at once (needed when CTAs wait for each other through global memory)
 inline void launch(unsigned grid, unsigned block, size_t smem_bytes, std::function<void()> body, int order = 0,
-                   bool interleave = false, size_t stack_bytes = 256 << 10)
+                   bool interleave = false, size_t stack_bytes = 256 << 10, unsigned grid_y = 1)
 {
+  for (unsigned by = 0; by < grid_y; ++by) {
+    simt_bid().y = by;
+    simt_gdim().y = grid_y;
     Scheduler S;
     sched() = &S;
     S.body = body;
@@ -199,6 +202,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, std::functi
         for (Cta& c : ctas) free(c.smem);
     }
     sched() = nullptr;
+  }
 }
 
 inline void cta_barrier()

@@ -152,3 +152,17 @@ def format_fields(png: Png) -> dict:
         r, g, b = struct.unpack(">HHH", png.trns[:6])
         out["key"] = (b, g, r) if png.cgbi else (r, g, b)
     return out
+
+
+def idat_chunks(data: bytes) -> list:
+    """the IDAT chunk bodies of a PNG file, one by one (the blocks the reference's Deflator handed to its encoder)"""
+    at, out = 8, []
+    while at < len(data):
+        (n,) = struct.unpack(">I", data[at:at + 4])
+        typ = data[at + 4:at + 8]
+        if typ == b"IDAT":
+            out.append(data[at + 8:at + 8 + n])
+        if typ == b"IEND":
+            break
+        at += 12 + n
+    return out

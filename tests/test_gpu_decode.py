@@ -208,9 +208,12 @@ def test_decode_error_mapping(pngb200, ctx, orc):
         assert g.status == st, (g.status, st)
     assert [g.status for g in got] == [pngb200.ERR_PNG_INCOMPLETE_DATASTREAM, pngb200.ERR_PNG_EXTRANEOUS_IMAGE_DATA,
                                        pngb200.OK, pngb200.ERR_PNG_EXTRANEOUS_IMAGE_DATA]
-    # the rows that were available are decoded
+    # the rows that were available are decoded, the missing one stays as PNG.Image.storage is initialised: zero
+    # (not the bytes of whatever image used the arena before -- decode a batch of noise first to dirty it)
     st, storage, _ = orc.png_decode(cases[2], w, h, 32, 8)
     assert got[2].pixels[: (h - 1) * w * 4] == storage[: (h - 1) * w * 4]
+    assert got[2].pixels[(h - 1) * w * 4:] == bytes(w * 4)
+    assert len(got[2].pixels) == h * w * 4
 
 
 def test_filter_batch_matches_oracle(pngb200, ctx, orc):

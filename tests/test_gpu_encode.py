@@ -74,3 +74,43 @@ def test_encode_decode_roundtrip_on_device(pngb200, ctx, orc):
             assert e[0] == 0 and a.status == 0 and a.pixels == f.pixels
             st, storage, _ = orc.png_decode(e[1], p.width, p.height, p.volume, p.depth, p.interlaced)
             assert st == 0 and storage == f.pixels
+
+
+def test_streaming_deflator_in_png_encoder_call_order(pngb200, ctx, orc):
+    """LZ77.Deflator.push(_:last:) / pop() / pull() used exactly as PNG.Encoder.pull uses them
+    (Sources/PNG/Encoding/PNG.Encoder.swift:68-128: one push per filtered scanline, pop() after every push,
+    push([], last: true) at the end, pull() until nil): the blocks are the reference's -- every complete block
+    2 * capacity = 65544 bytes, the concatenation the level-9 stream of the committed output"""
+    name = KEPT[0]
+    out = pngio.parse(open(os.path.join(GOLDEN, "encode", "out-" + name), "rb").read())
+    base = pngio.parse(open(os.path.join(GOLDEN, "encode", "in-" + name), "rb").read())
+    storage = pngb200.decode_batch(ctx, [dict(idat=base.idat, width=base.width, height=base.height, volume=base.volume,
+                                              depth=base.depth, interlaced=base.interlaced)])[0].pixels
+    (filtered,) = pngb200.filter_batch(ctx, [dict(pixels=storage, width=out.width, height=out.height, volume=out.volume,
+                                                  depth=out.depth, interlaced=out.interlaced)])
+    pitch1 = len(filtered) // out.height
+    z = pngb200.Deflator(ctx, pngb200.FORMAT_ZLIB, level=9)
+    blocks = []
+    for y in range(out.height):
+        z.push(filtered[y * pitch1:(y + 1) * pitch1])
+        while (b := z.pop()) is not None:
+            blocks.append(b)
+    z.push(b"", last=True)
+    while (b := z.pull()) is not None:
+        blocks.append(b)
+    assert z.pop() is None and z.pull() is None
+    z.close()
+    assert b"".join(blocks) == out.idat == orc.deflate(filtered, 9)
+    assert all(len(b) == 65544 for b in blocks[:-1]) and 0 < len(blocks[-1]) <= 65544
+    # the IDAT chunks of the committed file are these very blocks
+    assert [len(b) for b in blocks] == [len(c) for c in pngio.idat_chunks(open(os.path.join(GOLDEN, "encode", "out-" + name), "rb").read())]
+    # a small chunk size and the gzip wrapper
+    data = corpus.make("photo", 96, 64, 5).tobytes()
+    z = pngb200.Deflator(ctx, pngb200.FORMAT_GZIP, level=10, chunk_bytes=1000)
+    z.push(data[:5000])
+    assert z.pop() is None
+    z.push(data[5000:], last=True)
+    parts = []
+    while (b := z.pull()) is not None:
+        parts.append(b)
+    assert b"".join(parts) == orc.deflate(data, 10, orc.GZIP) and all(len(p) == 1000 for p in parts[:-1])
