@@ -39,6 +39,24 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner ...) goes to
+    stderr from now on; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,6 +201,7 @@ def peaks():
 
 def main():
     args = parse_args()
+    quiet_stdout()
     w, h, sixteen, dbatch, dunique = WORKLOADS[args.workload]
     args.batch = args.batch or dbatch
     args.unique = min(args.unique or dunique, args.batch)
@@ -220,7 +239,7 @@ def main():
                                  "sample": f"{per_step} images per step, {threads} host threads, C restatement "
                                            "of the Swift reference (no Swift toolchain in the image)"},
                 "e2e": {"value": v, "unit": "MPixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(json.dumps(line))
         return
 
     if args.mode == "encode":
@@ -485,7 +504,7 @@ def main():
             "config": config, "clocks": clocks.summary(), "gpu_launches": int(launches),
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "bit_exact": True, "small_batch": small,
             "inflate_stats_per_step": stats}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -545,7 +564,7 @@ def main_inflate(args, rank, local_rank, world):
         del d_src
     if rank == 0:
         best = max(r["c_plus_u_GBps"] for r in rows)
-        print(json.dumps({"metric": "GB/s standalone gzip inflate (C+U)", "value": best, "unit": "GB/s", "n_gpus": world,
+        emit(json.dumps({"metric": "GB/s standalone gzip inflate (C+U)", "value": best, "unit": "GB/s", "n_gpus": world,
                           "steps": args.steps, "warmup": 2, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "u8", "data": "synthetic",
                           "config": {"workload": "gzip streams of S0 filtered bytes, zlib level 6 (BASELINE configs[4])"},
@@ -581,7 +600,7 @@ def main_encode(args, w, h, bpp, depth, rank, local_rank, world, config):
                 list(ex.map(one, range(per_step)))
         dt = time.perf_counter() - t0
         v = args.steps * per_step * npix / dt / 1e6
-        print(json.dumps({"impl": "reference", "metric": "MPixels/s encode (filter+deflate)", "value": v,
+        emit(json.dumps({"impl": "reference", "metric": "MPixels/s encode (filter+deflate)", "value": v,
                           "unit": "MPixels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
@@ -653,7 +672,7 @@ def main_encode(args, w, h, bpp, depth, rank, local_rank, world, config):
             "cpu_baseline": {"value": npix / cpu_dt / 1e6, "unit": "MPixels/s", "cores": 1, "kind": "port",
                              "sample": f"1 image of the same workload on 1 host thread in {cpu_dt:.1f}s (oracle/)"},
             "bit_exact": True, "compression_ratio": B * storage_bytes / comp}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -123,8 +123,35 @@ constexpr int WAVE_WARPS   = 8;
 #endif
 constexpr int WAVE_PUBLISH = PNGB200_WAVE_PUBLISH;  // publish progress every this many chunks
 
+// Asynchronous staging of a lane's own row (cp.async = LDGSTS: global -> shared memory without a register in
+// between).  Every lane keeps WAVE_DEPTH aligned 16-byte chunks of its row in flight in a private ring in shared
+// memory, so the HBM / L2 round trip of chunk j + WAVE_DEPTH overlaps the arithmetic of chunks j .. j + WAVE_DEPTH - 1
+// (r01: two chunks ahead in registers, 11.7 long-scoreboard stall cycles per issue).
+constexpr int WAVE_DEPTH = 8;
+__device__ __forceinline__ void cp_async16(uint4* smem, const uint4* gmem)
+{
+#ifdef PNGB200_EMU
+    *smem = *gmem;
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+#ifndef PNGB200_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()   // at most N of this thread's groups still in flight
+{
+#ifndef PNGB200_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 template <int BPP>
-__device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_prev, uint32_t* prog_mine)
+__device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_prev, uint32_t* prog_mine, uint4 (*ring)[32])
 {
     const unsigned lane   = lane_id();
     const uint32_t y      = band * 32 + lane;
@@ -157,12 +184,15 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
     uint32_t seen = 0;
     uint4    upn = make_uint4(0, 0, 0, 0);  // lane 0: the chunk of the row above for the next step
     bool     upn_ok = false;
-    // input chunks are fetched two steps ahead of their use (qcur = chunk j, qnext = j + 1, qfar = j + 2)
-    // and the line after next is pulled into L2: with ~40 warps x 32 rows per SM the rows' lines do not
-    // survive in L1 (3 % hit rate under ncu), so every load is an L2 round trip that has to be hidden
-    uint4 qnext = make_uint4(0, 0, 0, 0);
-    if (active && nq > 0) qcur = inq[0];
-    if (active && nq > 1) qnext = inq[1];
+    // input chunk k of my row is cp.async group k of this thread: WAVE_DEPTH groups are opened here, one more per
+    // step, so when chunk j is consumed the groups up to j + 1 must have landed = at most WAVE_DEPTH - 2 in flight
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < WAVE_DEPTH; ++k) {
+            if (k < nq) cp_async16(&ring[k][lane], inq + k);
+            cp_async_commit();
+        }
+    }
 
     for (int S = 0; S < nchunk + 32; ++S) {
         const int j = S - (int)lane;
@@ -196,12 +226,13 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
             }
         }
         if (active && j >= 0 && j < nchunk) {
-            uint4 qfar = make_uint4(0, 0, 0, 0);
-            if (j + 2 < nq) qfar = inq[j + 2];
-            if ((j & 7) == 0 && j + 24 < nq) asm volatile("prefetch.global.L2 [%0];" ::"l"(inq + j + 24));
+            cp_async_wait<WAVE_DEPTH - 2>();
+            qcur = ring[j % WAVE_DEPTH][lane];
+            const uint4 qnext = ring[(j + 1) % WAVE_DEPTH][lane];
             uint4 x = m == 0 ? qcur : shift_bytes(qcur, qnext, m);
-            qcur = qnext;
-            qnext = qfar;
+            // chunk j + WAVE_DEPTH takes the slot chunk j just left (x depends on the loads above: they are done)
+            if (j + WAVE_DEPTH < nq) cp_async16(&ring[j % WAVE_DEPTH][lane], inq + j + WAVE_DEPTH);
+            cp_async_commit();
             uint4 o;
             if (BPP == 4) {
                 o.x = __vadd4(x.x, predict4(type, a1, up.x, c1, any_paeth));
@@ -247,10 +278,14 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
             }
         }
     }
+    cp_async_wait<0>();   // nothing of this band may still land in the ring when the warp takes its next band
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(WAVE_WARPS * 32) unfilter_wave_kernel(WaveParams p)
 {
+    __shared__ uint4 rings[WAVE_WARPS][WAVE_DEPTH][32];   // [warp][slot][lane]: conflict-free 16-byte accesses
+    uint4 (*ring)[32] = rings[threadIdx.x >> 5];
     const unsigned lane = lane_id();
     for (;;) {
         uint32_t t = 0;
@@ -270,12 +305,12 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) unfilter_wave_kernel(WavePara
         uint32_t*      prev  = band == 0 ? nullptr : p.progress + t - 1;
         uint32_t*      mine  = band + 1 < nband ? p.progress + t : nullptr;
         switch (job.bpp) {
-        case 1: wave_band<1>(job, band, prev, mine); break;
-        case 2: wave_band<2>(job, band, prev, mine); break;
-        case 3: wave_band<3>(job, band, prev, mine); break;
-        case 4: wave_band<4>(job, band, prev, mine); break;
-        case 6: wave_band<6>(job, band, prev, mine); break;
-        default: wave_band<8>(job, band, prev, mine); break;
+        case 1: wave_band<1>(job, band, prev, mine, ring); break;
+        case 2: wave_band<2>(job, band, prev, mine, ring); break;
+        case 3: wave_band<3>(job, band, prev, mine, ring); break;
+        case 4: wave_band<4>(job, band, prev, mine, ring); break;
+        case 6: wave_band<6>(job, band, prev, mine, ring); break;
+        default: wave_band<8>(job, band, prev, mine, ring); break;
         }
     }
 }
