@@ -474,17 +474,24 @@ def main():
     inflate_kernel = "inflate_wave_kernel" if B <= 296 else "inflate_parallel_kernel"  # pngb200_api.cu run_inflate
     names = [inflate_kernel, "checksum kernels", "unfilter_wave_kernel"]
     achieved = alg_bytes / (stage[0] / 1e3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        entry = json.load(open(tpath)).get(args.workload)
-        if entry and entry.get("batch") == B and args.encoder == "zlib" and args.kind == "photo":
-            traffic = entry["bytes_per_launch"]  # measured once under ncu for exactly this launch shape
+        for entry in json.load(open(tpath)).get(args.workload) or []:
+            if entry.get("batch") == B and entry.get("kernel") == inflate_kernel and args.encoder == "zlib" and args.kind == "photo":
+                traffic = entry["bytes_per_launch"]  # measured once under ncu for exactly this launch shape
+                if entry.get("warp_instructions_per_launch"):
+                    # issue roofline beside the HBM one: warp instructions of the launch (ncu) over what the
+                    # SMs' 4 schedulers can issue in the measured time at the sampled SM clock
+                    clk = (clocks.summary().get("sm_mhz") or 1965.0) * 1e6
+                    issue = {"warp_instructions_per_launch": entry["warp_instructions_per_launch"],
+                             "per_output_byte": entry["warp_instructions_per_launch"] / (B * pkg.filtered_size(w, h, 8 * bpp)),
+                             "frac": entry["warp_instructions_per_launch"] / (148 * 4 * clk * stage[0] / 1e3)}
     roofline = {"bound": "hbm", "kernel": names[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "stage_ms": {"inflate": stage[0], "checksum": stage[1], "unfilter": stage[2]},
-                "dominant_stage": names[dominant],
+                "dominant_stage": names[dominant], "issue_roofline": issue,
                 "whole_step_frac": alg_bytes / (ms_max / args.steps / 1e3) / 1e9 / peak}
 
     cpu = None

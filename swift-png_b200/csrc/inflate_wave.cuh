@@ -130,6 +130,7 @@ struct WvShared {
     uint32_t     exc[WV_WARPS], valid[WV_WARPS];
     uint32_t     last, term, anomaly, ticket;
     uint64_t     cyc[12], tick;                 // phase timers (thread 0)
+    uint64_t     pf_bar;                        // mbarrier of the bulk prefetch (lands in mask[] .. ck[], dead by then)
     WvHeader     hdr;
 };
 
@@ -181,6 +182,45 @@ __device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 #endif
+
+// ---- bulk asynchronous copy (TMA, 1-D) global -> shared memory, completion on an mbarrier ----
+// The next wave's 8 KiB of compressed words are fetched by the copy engine while this wave is still being emitted,
+// resolved and stored: the HBM round trip of the stage phase (8.4 K cycles per wave, round-2 counters) leaves the
+// critical path.  One elected thread issues, everybody waits on the mbarrier's phase parity.
+#ifdef PNGB200_EMU
+inline void mbar_init(uint64_t*, uint32_t) {}
+inline void mbar_expect_tx(uint64_t*, uint32_t) {}
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
+inline bool mbar_try_wait(uint64_t*, uint32_t) { return true; }
+inline void fence_proxy_async() {}
+#else
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+constexpr uint32_t WV_PF_WORDS = WV_WORDS + 4;   // prefetched words: the wave + up to 3 words of 16-byte alignment slack
 
 // register look-ahead bit reader over the staged (padded) words
 struct FastBits {
@@ -607,6 +647,10 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
     uint32_t* const gbitmap = reinterpret_cast<uint32_t*>(P.scratch + blockIdx.x * P.scratch_stride +
                                                          sizeof(CopyItem) * WV_LIST_CAP);
     for (uint32_t k = t; k < WV_BITMAP_WORDS; k += WV_THREADS) sh.bitmap[k] = 0;
+    if (t == 0) mbar_init(&sh.pf_bar, 1);
+    static_assert(offsetof(WvShared, ck) == offsetof(WvShared, mask) + sizeof(uint32_t) * 8 * WV_THREADS, "prefetch area = mask ++ ck");
+    static_assert(sizeof(uint32_t) * WV_PF_WORDS <= 2 * sizeof(uint32_t) * 8 * WV_THREADS && offsetof(WvShared, mask) % 16 == 0, "prefetch area");
+    uint32_t pf_parity = 0;          // phase of the mbarrier the next wait looks for
     const saddr_t words_addr = smem_addr(sh.words);
     const saddr_t lit = smem_addr(sh.ser.lit), dstt = smem_addr(sh.ser.dist);
     uint32_t* const mk = sh.mask;
@@ -639,6 +683,8 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
         const uint32_t mis = (uint32_t)((uintptr_t)dst & 15);  // ring position = stream offset + mis (mod 65536)
         bool fallback = false;
         bool ring_stale = job.start_out != 0;   // the ring does not hold the window [out - 32768, out)
+        bool     pf_pending = false;            // a bulk prefetch is in flight / has landed
+        uint64_t pf_first = 0;                  // first word (reader space) of the prefetched range
         // running Adler-32 (thread 0): valid when this launch sees the stream from its first byte
         const bool adler_on = job.start_out == 0 && !sym;
         uint32_t   s1 = 1, s2 = 0;
@@ -745,8 +791,22 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                     const uint64_t wstart = br.pos;                       // absolute bit (reader space)
                     const uint64_t wbase  = (wstart >> 5) & ~(uint64_t)7; // first staged word
                     __syncthreads();
-                    for (uint32_t k = t; k < WV_WORDS; k += WV_THREADS)
-                        sh.words[k + (k >> 3)] = br.load_word(wbase + k);
+                    bool staged = false;
+                    if (pf_pending) {
+                        // the words the copy engine fetched while the previous wave was emitted (always waited
+                        // for: the landing zone is about to become the token maps again)
+                        while (!mbar_try_wait(&sh.pf_bar, pf_parity)) {}
+                        pf_parity ^= 1;
+                        pf_pending = false;
+                        if (wbase >= pf_first && wbase - pf_first < 4) {
+                            const uint32_t* lin = sh.mask + (uint32_t)(wbase - pf_first);
+                            for (uint32_t k = t; k < WV_WORDS; k += WV_THREADS) sh.words[k + (k >> 3)] = lin[k];
+                            staged = true;
+                        }
+                    }
+                    if (!staged)
+                        for (uint32_t k = t; k < WV_WORDS; k += WV_THREADS)
+                            sh.words[k + (k >> 3)] = br.load_word(wbase + k);
                     if (t == 0) sh.wcount[0] = 0;
                     __syncthreads();                                      // (1)
                     fold_adler();
@@ -998,6 +1058,21 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                         break;
                     }
                     const uint32_t  total  = (uint32_t)total64;
+                    // ---- the next wave will almost always start in the word after this one's last: fetch its words
+                    //      now (bulk async copy into the token maps' memory, which is dead until the next phase A) ----
+                    {
+                        const uint64_t nbase = wbase + WV_BITS / 32;                       // predicted first staged word
+                        const uint64_t first = nbase - ((((uintptr_t)br.words >> 2) + nbase) & 3);   // 16-byte aligned address
+                        if (first >= 1 && (first + WV_PF_WORDS + 1) * 32 <= br.total_bits) {
+                            if (t == 0) {
+                                fence_proxy_async();   // the maps were read and written through the generic proxy
+                                mbar_expect_tx(&sh.pf_bar, sizeof(uint32_t) * WV_PF_WORDS);
+                                bulk_g2s(sh.mask, br.words + first, sizeof(uint32_t) * WV_PF_WORDS, &sh.pf_bar);
+                            }
+                            pf_pending = true;
+                            pf_first = first;
+                        }
+                    }
                     // ---- E. emit: decode my share once more and write it ----
                     uint8_t* const  wdst   = dst + out * esz;     // HBM address of wave offset 0
                     const bool      in_hbm = sym || total > WV_OUT_BYTES;
@@ -1184,6 +1259,11 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                 st = read_trailer(br, job.format, r);
                 break;
             }
+        }
+        if (pf_pending) {   // nothing may still land in shared memory when the CTA turns to its next stream
+            while (!mbar_try_wait(&sh.pf_bar, pf_parity)) {}
+            pf_parity ^= 1;
+            pf_pending = false;
         }
         __syncthreads();
         fold_adler();

@@ -38,7 +38,10 @@ def _worker(rank, world, port, q):
         return out
 
     res = shard.run_sharded([len(s) for s in streams], work)
-    q.put((rank, res))
+    # the benchmark's layout: rank-major, the same number of jobs on every rank, no LPT
+    eq_sizes = [7, 8, 9, 7, 8, 9]
+    eq = shard.run_sharded(eq_sizes, lambda idxs: [(0, 100 * rank + i, eq_sizes[i]) for i in idxs], equal_shards=3)
+    q.put((rank, (res, eq)))
     dist.destroy_process_group()
 
 
@@ -59,4 +62,6 @@ def test_sharded_run_over_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     expect = [(0, zlib.adler32(bytes([i]) * (1000 * (i + 1))), 1000 * (i + 1)) for i in range(9)]
-    assert got[0] == expect and got[1] == expect
+    assert got[0][0] == expect and got[1][0] == expect
+    eq = [(0, 0, 7), (0, 1, 8), (0, 2, 9), (0, 103, 7), (0, 104, 8), (0, 105, 9)]
+    assert got[0][1] == eq and got[1][1] == eq
