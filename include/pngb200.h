@@ -139,6 +139,11 @@ int          pngb200_ctx_inflate_counters(pngb200_ctx* ctx, size_t count, uint64
  * decode batch on this context: out[0] streams that were cut, out[1] segments they were cut into, out[2] streams
  * whose segments did not line up and that were decoded whole after all (results are identical either way). */
 int          pngb200_ctx_segment_stats(pngb200_ctx* ctx, uint64_t out[3]);
+/* scanlines per filter type of the last decode / unfilter batch that went through the wavefront kernel
+ * (non-interlaced, >= 8 bits per sample): out[0..4] = None, Sub, Up, Average, Paeth, out[5] = rows with an
+ * invalid filter byte (left unchanged, as the reference does).  The device-side form of the reference's
+ * -DDUMP_FILTERED_SCANLINES output (Sources/PNG/Decoding/PNG.Decoder.swift:96-98,128). */
+int          pngb200_ctx_filter_histogram(pngb200_ctx* ctx, uint64_t out[6]);
 /* inflate_mode: 0 automatic; 1 one warp per stream; 2 a whole CTA per stream, never cut; 3 / 4 force the
  * ring-window / the round-1 intra-stream kernel; 5 as 0 */
 

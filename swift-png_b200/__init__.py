@@ -232,6 +232,8 @@ def lib():
     for fn in (L.pngb200_deflator_pop, L.pngb200_deflator_pull):
         fn.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
         fn.restype = C.c_int
+    L.pngb200_ctx_filter_histogram.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.pngb200_ctx_filter_histogram.restype = C.c_int
     L.pngb200_ctx_segment_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_segment_stats.restype = C.c_int
     L.pngb200_ctx_inflate_counters.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
@@ -341,6 +343,12 @@ class Context:
         return dict(waves=out[0], walk_tokens=out[1], resolve_rounds=out[2], fallbacks=out[3], tokens=out[4],
                     matches=out[5], deferred_matches=out[6], blocks=out[7],
                     cycles={n: out[8 + i] for i, n in enumerate(names)})
+
+    def filter_histogram(self):
+        """scanlines per filter type (None, Sub, Up, Average, Paeth, invalid) of the last wavefront-unfilter batch"""
+        out = (C.c_uint64 * 6)()
+        self.check(self._lib.pngb200_ctx_filter_histogram(self.handle, out))
+        return list(out)
 
     def segment_stats(self):
         """(streams cut into segments, segments, streams decoded whole after all) of the last batch"""

@@ -107,6 +107,8 @@ struct pngb200_ctx {
     uint64_t seg_streams = 0, seg_segments = 0, seg_fallbacks = 0;  // last batch: streams cut into segments, segments, rejected
     uint64_t scratch_stride = 0;       // layout of d_scratch the last inflate launch used
     size_t parallel_threshold = 8192;  // streams at least this long use the block-parallel kernel
+    unsigned long long* d_hist = nullptr;   // filter-type histogram of the last wavefront-unfilter launch (in d_imgjobs)
+    size_t peer_streams = 0;           // lanes: streams of the whole host batch (its chunks run side by side on this GPU)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // decode stage boundaries
     // geometry of the pending decode batch
     std::vector<uint64_t> expected;   // filtered bytes expected per image
@@ -404,7 +406,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
         if (ctx->inflate_mode == 0 || ctx->inflate_mode == 5) {
             // few big streams: cut them so that every CTA slot has something to decode
             const size_t before = par.size();
-            if (!par.empty() && par.size() * 2 <= (size_t)ctx->sm_count * WV_CTAS_PER_SM) {
+            if (!par.empty() && std::max(par.size(), ctx->peer_streams) * 2 <= (size_t)ctx->sm_count * WV_CTAS_PER_SM) {
                 if (int rc = before_first_launch()) return rc;
                 hooked = true;
                 if (int rc = run_segments(ctx, h_jobs, par)) return rc;
@@ -427,7 +429,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             //    SM.  Slower per stream, but twice the streams in flight hide its barrier phases: measured r02 on
             //    8K RGBA8 1.96 ms per image against 2.51 ms once a batch exceeds the wave kernel's slots.
             const size_t wave_slots = (size_t)ctx->sm_count * WV_CTAS_PER_SM;
-            bool use_wave = par.size() <= wave_slots;
+            bool use_wave = std::max(par.size(), ctx->peer_streams) <= wave_slots;   // (lanes: the chunks of a host batch run side by side)
             if (ctx->inflate_mode == 3) use_wave = true;
             if (ctx->inflate_mode == 4) use_wave = false;
             const uint64_t bitmap_words = use_wave ? wv_bitmap_words(max_cap) : par_bitmap_words(max_cap);
@@ -565,6 +567,8 @@ struct UnfilterItem {
 
 int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
 {
+    ctx->d_hist = nullptr;
+
     std::vector<ImageJob>   fast;
     std::vector<GenericJob> slow;
     std::vector<uint32_t>   band_base;
@@ -606,7 +610,7 @@ int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
     if (!fast.empty()) {
         size_t jb = sizeof(ImageJob) * fast.size(), bb = sizeof(uint32_t) * band_base.size();
         size_t off_bb = align_up(jb, 256), off_pr = align_up(off_bb + bb, 256);
-        size_t total = off_pr + sizeof(uint32_t) * (bands + 1);
+        size_t total = align_up(off_pr + sizeof(uint32_t) * (bands + 1), 8) + 8 * sizeof(unsigned long long);
         CU(ctx->h_imgjobs.reserve(off_pr));
         CU(ctx->d_imgjobs.reserve(total));
         memcpy(ctx->h_imgjobs.p, fast.data(), jb);
@@ -618,6 +622,9 @@ int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
         p.band_base = (const uint32_t*)((char*)ctx->d_imgjobs.p + off_bb);
         p.progress = (uint32_t*)((char*)ctx->d_imgjobs.p + off_pr);
         p.ticket = p.progress + bands;
+        p.hist = (unsigned long long*)((char*)ctx->d_imgjobs.p + align_up(off_pr + sizeof(uint32_t) * (bands + 1), 8));
+        CU(cudaMemsetAsync(p.hist, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        ctx->d_hist = p.hist;
         p.njobs = (uint32_t)fast.size();
         p.total_bands = (uint32_t)bands;
         unsigned grid = (unsigned)std::min<uint64_t>((bands + WAVE_WARPS - 1) / WAVE_WARPS,
@@ -653,6 +660,8 @@ int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
 template <typename BytesOf, typename Work>
 int run_over_lanes(pngb200_ctx* ctx, size_t count, int memspace, BytesOf bytes_of, Work work)
 {
+    for (pngb200_ctx* lane : ctx->lanes) lane->d_hist = nullptr;   // counters describe the batch that starts now
+    ctx->d_hist = nullptr;
     size_t bytes = 0;
     for (size_t i = 0; i < count; ++i) bytes += bytes_of(i);
     // tunable for experiments: PNGB200_LANES, PNGB200_CHUNKS_PER_LANE (0 / unset = the rule above); read once
@@ -690,6 +699,7 @@ int run_over_lanes(pngb200_ctx* ctx, size_t count, int memspace, BytesOf bytes_o
             pngb200_ctx* lane = ctx->lanes[l];
             lane->inflate_mode = ctx->inflate_mode;
             lane->parallel_threshold = ctx->parallel_threshold;
+            lane->peer_streams = count;
             for (size_t c = l; c < nchunks; c += kLanes) {
                 size_t lo = cut[c], n = cut[c + 1] - cut[c];
                 if (n == 0) continue;
@@ -851,6 +861,23 @@ int pngb200_ctx_inflate_counters(pngb200_ctx* ctx, size_t count, uint64_t out[24
         out[6] += r[i].stat_deferred;
         out[7] += r[i].blocks;
         for (int k = 0; k < 12; ++k) out[8 + k] += r[i].stat_cycles[k];
+    }
+    return PNGB200_OK;
+}
+
+int pngb200_ctx_filter_histogram(pngb200_ctx* ctx, uint64_t out[6])
+{
+    if (!ctx || !out) return PNGB200_ERR_BAD_ARGUMENT;
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    DeviceGuard guard(ctx->device);
+    std::vector<pngb200_ctx*> all{ctx};
+    all.insert(all.end(), ctx->lanes.begin(), ctx->lanes.end());
+    for (pngb200_ctx* c : all) {
+        if (!c->d_hist) continue;
+        unsigned long long h[6];
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemcpy(h, c->d_hist, sizeof h, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 6; ++k) out[k] += h[k];
     }
     return PNGB200_OK;
 }
@@ -1592,8 +1619,13 @@ static int inflator_grow_out(pngb200_inflator* z, size_t need)
     if (need <= z->d_out.cap) return PNGB200_OK;
     DevBuf bigger;
     CU(bigger.reserve(std::max(need, z->d_out.cap * 2)));
-    if (z->produced) CU(cudaMemcpyAsync(bigger.p, z->d_out.p, z->produced, cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaSuccess;
+    if (z->produced) e = cudaMemcpyAsync(bigger.p, z->d_out.p, z->produced, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        bigger.release();   // not adopted: give it back
+        return set_error(ctx, PNGB200_ERR_CUDA, "inflator: growing the output failed: %s", cudaGetErrorString(e));
+    }
     z->d_out.release();
     z->d_out = bigger;
     return PNGB200_OK;

@@ -115,6 +115,8 @@ struct WaveParams {
     uint32_t*       ticket;
     uint32_t        njobs;
     uint32_t        total_bands;
+    unsigned long long* hist;   // [6]: scanlines per filter type 0..4, [5] = invalid filter bytes (the reference's
+                                // -DDUMP_FILTERED_SCANLINES view of a decode, PNG.Decoder.swift:96-98,128); may be null
 };
 
 constexpr int WAVE_WARPS   = 8;
@@ -151,7 +153,8 @@ __device__ __forceinline__ void cp_async_wait()   // at most N of this thread's 
 }
 
 template <int BPP>
-__device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_prev, uint32_t* prog_mine, uint4 (*ring)[32])
+__device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_prev, uint32_t* prog_mine, uint4 (*ring)[32],
+                          unsigned long long* hist)
 {
     const unsigned lane   = lane_id();
     const uint32_t y      = band * 32 + lane;
@@ -161,6 +164,14 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
     const int      nchunk = (int)((pitch + 15) >> 4);
     const uint8_t* row    = job.filtered + (uint64_t)(active ? y : 0) * (pitch + 1);
     uint32_t       type   = active ? row[0] : 0;
+    if (hist != nullptr) {   // filter-type histogram of the batch: one atomic per type per band
+        const uint32_t raw = active ? min(type, 5u) : 6u;
+#pragma unroll
+        for (uint32_t k = 0; k < 6; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, raw == k);
+            if (lane == 0 && m) atomicAdd(hist + k, (unsigned long long)__popc(m));
+        }
+    }
     if (type > 4) type = 0;  // invalid filter byte: row unchanged (PNG.Decoder.swift:193-194)
     const bool any_paeth = __any_sync(0xffffffffu, type == 4);
     const uint8_t* in    = row + 1;
@@ -305,12 +316,12 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) unfilter_wave_kernel(WavePara
         uint32_t*      prev  = band == 0 ? nullptr : p.progress + t - 1;
         uint32_t*      mine  = band + 1 < nband ? p.progress + t : nullptr;
         switch (job.bpp) {
-        case 1: wave_band<1>(job, band, prev, mine, ring); break;
-        case 2: wave_band<2>(job, band, prev, mine, ring); break;
-        case 3: wave_band<3>(job, band, prev, mine, ring); break;
-        case 4: wave_band<4>(job, band, prev, mine, ring); break;
-        case 6: wave_band<6>(job, band, prev, mine, ring); break;
-        default: wave_band<8>(job, band, prev, mine, ring); break;
+        case 1: wave_band<1>(job, band, prev, mine, ring, p.hist); break;
+        case 2: wave_band<2>(job, band, prev, mine, ring, p.hist); break;
+        case 3: wave_band<3>(job, band, prev, mine, ring, p.hist); break;
+        case 4: wave_band<4>(job, band, prev, mine, ring, p.hist); break;
+        case 6: wave_band<6>(job, band, prev, mine, ring, p.hist); break;
+        default: wave_band<8>(job, band, prev, mine, ring, p.hist); break;
         }
     }
 }

@@ -386,3 +386,23 @@ def test_segmented_stream_errors_fall_back(pngb200, ctx, orc):
         assert st == ost, (st, ost)
         if st == 0:
             assert out == oout
+
+
+def test_filter_type_histogram_counter(pngb200, ctx, orc):
+    """the device-side form of the reference's -DDUMP_FILTERED_SCANLINES dump: scanlines per filter type of a batch"""
+    rng = np.random.default_rng(77)
+    w, h = 200, 150
+    jobs, want = [], np.zeros(6, dtype=np.int64)
+    for k in range(3):
+        rows = rng.integers(0, 256, size=(h, w * 4 + 1), dtype=np.uint8)
+        rows[:, 0] = rng.integers(0, 5, size=h)
+        rows[7 * k, 0] = 9          # an invalid filter byte: the row is left as it is (PNG.Decoder.swift:193-194)
+        for v in rows[:, 0]:
+            want[min(int(v), 5)] += 1
+        jobs.append(dict(idat=zlib.compress(rows.tobytes(), 6), width=w, height=h, volume=32, depth=8, interlaced=0, fmt=0))
+    got = pngb200.decode_batch(ctx, jobs)
+    assert all(g.status == 0 for g in got)
+    assert ctx.filter_histogram() == [int(x) for x in want]
+    for j, g in zip(jobs, got):
+        st, storage, _ = orc.png_decode(j["idat"], w, h, 32, 8)
+        assert st == 0 and storage == g.pixels
