@@ -84,6 +84,7 @@ struct ParShared {
     uint64_t     warp_sums[32];
     uint32_t     first_need[2], first_stop[2], nlist[2];
     uint32_t     npend, anomaly, ticket, pad;
+    uint64_t     cyc[12], tick;         // phase timers (thread 0), as in inflate_wave_kernel
     ParHeader    hdr;
 };
 
@@ -222,7 +223,19 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
         if (t == 0) {
             sh.ticket = atomicAdd(P.ticket, 1u);
             sh.anomaly = 0;
+            for (int k = 0; k < 12; ++k) sh.cyc[k] = 0;
+            sh.tick = (uint64_t)clock64();
         }
+// thread 0 charges the cycles since the last tick to phase i: 0 header+tables, 1 stage, 3 speculate + re-decode
+// rounds, 5 scan, 6 emit, 7 resolve, 8 store
+#define PAR_TICK(i)                                          \
+    do {                                                     \
+        if (t == 0) {                                        \
+            const uint64_t now_ = (uint64_t)clock64();       \
+            sh.cyc[i] += now_ - sh.tick;                     \
+            sh.tick = now_;                                  \
+        }                                                    \
+    } while (0)
         __syncthreads();
         if (sh.ticket >= (uint32_t)P.count) return;
         const int       j   = P.order ? (int)P.order[sh.ticket] : (int)sh.ticket;
@@ -279,6 +292,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                 st = build_block_tables(&sh.ser, r, hdr.nlit, hdr.ndist, (int)t, PAR_THREADS);
                 if (st != PNGB200_OK) break;
             }
+            PAR_TICK(0);
             if (type == 0) {
                 if (!br.have(8 * (uint64_t)stored)) { st = PNGB200_NEED_MORE_INPUT; break; }
                 if (out + stored > job.dst_cap) { st = fail(r, PNGB200_ERR_OUTPUT_CAPACITY); break; }
@@ -304,6 +318,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         sh.nlist[0] = sh.nlist[1] = 0;
                     }
                     __syncthreads();
+                    PAR_TICK(1);
                     const uint32_t rel0  = (uint32_t)(wstart - (wbase << 5));  // < 256
                     const uint32_t limit = (t + 1) * PAR_SUB_BITS;
                     {
@@ -360,6 +375,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         }
                     }
                     __syncthreads();
+                    PAR_TICK(3);
                     const uint32_t my_start = sh.start_[t], n = sh.nout_[t];
                     // ---- anomalies on the verified chain -> serial decoder ----
                     if (t == nvalid - 1 && ((sh.flag_[t] & PF_BAD) || (wbase << 5) + sh.exit_[t] > br.total_bits))
@@ -383,6 +399,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         if (lane == PAR_WARPS - 1) sh.warp_sums[PAR_WARPS] = wi;  // wave totals
                     }
                     __syncthreads();
+                    PAR_TICK(5);
                     const uint64_t excl    = sh.warp_sums[warp] + incl - mine;
                     const uint32_t o_start = (uint32_t)(excl & 0xffffffffffull);
                     uint32_t       c_next  = (uint32_t)(excl >> 40);           // my first list slot
@@ -444,6 +461,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     }
                     __threadfence_block();
                     __syncthreads();
+                    PAR_TICK(6);
                     // ---- resolve: no CTA barriers.  The list is sorted by output offset and a copy only
                     //      depends on smaller offsets, so a lane may simply block on its current item
                     //      (items t, t + 512, ... in order): the smallest open item is always ready ----
@@ -490,6 +508,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     }
                     __threadfence_block();
                     __syncthreads();
+                    PAR_TICK(7);
                     if (sh.anomaly) {
                         // leave the bitmap clean for whoever uses it next
                         for (uint32_t k = t; k < (total + 31) / 32; k += PAR_THREADS) U[k] = 0;
@@ -511,6 +530,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                             }
                         }
                     }
+                    PAR_TICK(8);
                     out += total;
                     br.seek((wbase << 5) + sh.exit_[nvalid - 1]);
                     if (stop_found) block_done = true;
@@ -540,6 +560,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
             r->phase         = phase;
         }
         if (t == 0) {
+            for (int k = 0; k < 12; ++k) r->stat_cycles[k] = sh.cyc[k];
             r->stat_waves          = waves;
             r->stat_sync_rounds    = sync_rounds;
             r->stat_resolve_rounds = resolve_rounds;
