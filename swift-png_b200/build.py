@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "--shared", "-Xcompiler", "-fPIC",
-           "-DPNGB200_BUILD", "-o", LIB] + sources()
+           "-DPNGB200_BUILD", "-o", LIB] + [f for f in os.environ.get("PNGB200_NVCC_FLAGS", "").split() if f] + sources()
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -409,6 +409,14 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         fallback = true;
                         break;
                     }
+                    // ---- the next wave will almost always start in the word after this one's last: ask the copy
+                    //      engine to pull its 8 KiB into L2 now (bulk prefetch), so the stage phase of the next
+                    //      wave does not wait for HBM ----
+                    {
+                        const uint64_t nbase = wbase + PAR_THREADS * PAR_SUB_WORDS;
+                        const uint64_t first = nbase - ((((uintptr_t)br.words >> 2) + nbase) & 3);   // 16-byte aligned
+                        if (t == 0 && first >= 1 && (first + WV_PF_WORDS + 1) * 32 <= br.total_bits) bulk_prefetch_l2(br.words + first, 4 * WV_PF_WORDS);
+                    }
                     // ---- emit: literals into the output image, copies onto the work list ----
                     uint8_t* const  wdst   = dst + out;           // HBM address of wave offset 0
                     const uint32_t  shift  = (uint32_t)((uintptr_t)wdst & 15);

@@ -76,6 +76,9 @@ constexpr uint32_t WV_LIST_CAP     = WV_BITS / 2 + 64;                  // >= co
 constexpr uint64_t WV_MAX_WAVE_OUT = (uint64_t)WV_LIST_CAP * 258;
 constexpr uint32_t WV_HDR_WORDS    = 192;                               // block header staging (<= 566 bytes)
 constexpr uint32_t ADLER_MOD32     = 65521;
+#ifndef WV_POLL_NS
+#define WV_POLL_NS 20
+#endif
 constexpr uint32_t WV_WALK_K       = 8;                                 // tokens per walk in round 0 (doubles)
 
 // cost model instrumentation (emulator builds only): loop trips per thread and per warp (max over lanes)
@@ -193,6 +196,7 @@ inline void mbar_expect_tx(uint64_t*, uint32_t) {}
 inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t*) { memcpy(dst, src, bytes); }
 inline bool mbar_try_wait(uint64_t*, uint32_t) { return true; }
 inline void fence_proxy_async() {}
+inline void bulk_prefetch_l2(const void*, uint32_t) {}
 #else
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
@@ -219,6 +223,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// bulk prefetch of `bytes` (multiple of 16, 16-byte aligned) into L2: one instruction for the copy engine, no completion to wait for
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 #endif
 constexpr uint32_t WV_PF_WORDS = WV_WORDS + 4;   // prefetched words: the wave + up to 3 words of 16-byte alignment slack
 
@@ -1190,7 +1199,7 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                             }
                             ++rounds;
                             if (!__any_sync(0xffffffffu, g < nd)) break;
-                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(20);
+                            if (!__any_sync(0xffffffffu, progressed)) __nanosleep(WV_POLL_NS);
                         }
                         resolve_rounds += rounds;
                         WV_COUNT(4, rounds);
