@@ -85,6 +85,11 @@ struct ParShared {
     uint32_t     first_need[2], first_stop[2], nlist[2];
     uint32_t     npend, anomaly, ticket, pad;
     uint64_t     cyc[12], tick;         // phase timers (thread 0), as in inflate_wave_kernel
+    // running Adler-32 of the stream (zlib / ios streams decoded from their first byte), folded wave by wave from the
+    // partial sums the store phase leaves here: no second pass over the inflated bytes (as in inflate_wave_kernel)
+    uint64_t     pend_len;
+    uint32_t     s1, s2, pend;
+    uint32_t     adler_a[PAR_WARPS], adler_b[PAR_WARPS];
     ParHeader    hdr;
 };
 
@@ -207,7 +212,9 @@ __device__ __forceinline__ void lz_copy(uint8_t* img, const uint8_t* hbm, bool i
     }
 }
 
-__global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel_kernel(ParParams P)
+// One body, two register budgets: 4 CTAs per SM (64 registers, a few spills) when there are streams for them, 3 CTAs
+// per SM (80 registers, none) when the batch only fills three slots per SM anyway -- the 444 x 8K benchmark batch.
+__device__ __forceinline__ void inflate_parallel_body(ParParams P)
 {
     PNGB200_DYN_SMEM(par_smem);
     ParShared& sh = *reinterpret_cast<ParShared*>(par_smem);
@@ -225,7 +232,21 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
             sh.anomaly = 0;
             for (int k = 0; k < 12; ++k) sh.cyc[k] = 0;
             sh.tick = (uint64_t)clock64();
+            sh.s1 = 1;
+            sh.s2 = 0;
+            sh.pend = 0;
         }
+// fold the partial sums of the piece that was stored last into (s1, s2); call right after a barrier
+#define PAR_FOLD_ADLER()                                                                                     \
+    do {                                                                                                     \
+        if (t == 0 && sh.pend) {                                                                             \
+            uint64_t A_ = 0, B_ = 0;                                                                         \
+            for (int w_ = 0; w_ < PAR_WARPS; ++w_) { A_ += sh.adler_a[w_]; B_ += sh.adler_b[w_]; }           \
+            sh.s2 = (uint32_t)((sh.s2 + (sh.pend_len % ADLER_MOD32) * sh.s1 + B_) % ADLER_MOD32);            \
+            sh.s1 = (uint32_t)((sh.s1 + A_) % ADLER_MOD32);                                                  \
+            sh.pend = 0;                                                                                     \
+        }                                                                                                    \
+    } while (0)
 // thread 0 charges the cycles since the last tick to phase i: 0 header+tables, 1 stage, 3 speculate + re-decode
 // rounds, 5 scan, 6 emit, 7 resolve, 8 store
 #define PAR_TICK(i)                                          \
@@ -251,6 +272,21 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
         uint64_t resume_bit = job.start_bit, resume_out = job.start_out;
         uint8_t* const dst = job.dst;
         bool fallback = false;
+        const bool adler_on = job.start_out == 0;   // this launch sees the stream from its first byte
+        // CTA-wide partial sums of `n` finished bytes at HBM address `p` (stored blocks, oversized waves)
+        auto adler_hbm = [&](const uint8_t* p, uint64_t n) {
+            uint64_t a = 0, bw = 0;
+            const uint64_t per = (n + PAR_THREADS - 1) / PAR_THREADS;
+            const uint64_t lo = min((uint64_t)t * per, n), hi = min(lo + per, n);
+            adler_bytes(p + lo, hi - lo, n - lo, a, bw);
+            uint32_t a32 = (uint32_t)(a % ADLER_MOD32), b32 = (uint32_t)(bw % ADLER_MOD32);
+            for (int o = 16; o; o >>= 1) {
+                a32 += __shfl_down_sync(0xffffffffu, a32, o);
+                b32 += __shfl_down_sync(0xffffffffu, b32, o);
+            }
+            if (lane == 0) { sh.adler_a[warp] = a32; sh.adler_b[warp] = b32; }
+            if (t == 0) { sh.pend = 1; sh.pend_len = n; }
+        };
 
         if (phase == 0) {
             st = read_stream_header(br, job.format, r);
@@ -264,6 +300,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
         while (st == PNGB200_OK && phase == 1) {
             // warp 0 walks the header bits alone; the CTA then builds the tables together
             __syncthreads();
+            PAR_FOLD_ADLER();
             {
                 const uint64_t hbase = br.pos >> 5;
                 for (uint32_t k = t; k < WV_HDR_WORDS; k += PAR_THREADS) sh.words[k] = br.load_word(hbase + k);
@@ -298,9 +335,11 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                 if (out + stored > job.dst_cap) { st = fail(r, PNGB200_ERR_OUTPUT_CAPACITY); break; }
                 const uint8_t* s = job.src + (br.at() >> 3);
                 for (uint32_t k = t; k < stored; k += PAR_THREADS) dst[out + k] = s[k];
+                if (adler_on && stored) adler_hbm(s, stored);
                 out += stored;
                 br.seek(br.pos + 8 * (uint64_t)stored);
                 __syncthreads();
+                PAR_FOLD_ADLER();
             } else {
                 bool block_done = false;
                 while (!block_done) {
@@ -309,6 +348,7 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                     const uint64_t wstart = br.pos;                       // absolute bit (reader space)
                     const uint64_t wbase  = (wstart >> 5) & ~(uint64_t)7; // first staged word
                     __syncthreads();
+                    PAR_FOLD_ADLER();
                     for (uint32_t k = t; k < PAR_WAVE_WORDS; k += PAR_THREADS)
                         sh.words[k + (k >> 3)] = br.load_word(wbase + k);
                     if (t == 0) {
@@ -529,14 +569,33 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                         const uint32_t       end  = shift + total;           // bytes [shift, end) are ours
                         const uint32_t       nq   = (end + 15) >> 4;
                         const uint4* const   q    = reinterpret_cast<const uint4*>(sh.outbuf);
+                        uint32_t a = 0, bw = 0;   // 32 bits are enough for one thread's chunks of a 16 KiB image
                         for (uint32_t c = t; c < nq; c += PAR_THREADS) {
                             const uint32_t lo = c << 4, hi = lo + 16;
                             if (lo >= shift && hi <= end) {
-                                reinterpret_cast<uint4*>(base)[c] = q[c];
+                                const uint4 x = q[c];
+                                reinterpret_cast<uint4*>(base)[c] = x;
+                                adler_chunk16_u32(x, end - lo, a, bw);
                             } else {
-                                for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) base[k] = sh.outbuf[k];
+                                for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) {
+                                    const uint8_t v = sh.outbuf[k];
+                                    base[k] = v;
+                                    a += v;
+                                    bw += (end - k) * v;
+                                }
                             }
                         }
+                        if (adler_on) {
+                            uint32_t a32 = a, b32 = bw % ADLER_MOD32;
+                            for (int o = 16; o; o >>= 1) {
+                                a32 += __shfl_down_sync(0xffffffffu, a32, o);
+                                b32 += __shfl_down_sync(0xffffffffu, b32, o);
+                            }
+                            if (lane == 0) { sh.adler_a[warp] = a32; sh.adler_b[warp] = b32; }
+                            if (t == 0) { sh.pend = 1; sh.pend_len = total; }
+                        }
+                    } else if (in_hbm && adler_on && total) {
+                        adler_hbm(wdst, total);
                     }
                     PAR_TICK(8);
                     out += total;
@@ -554,6 +613,8 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
                 break;
             }
         }
+        __syncthreads();
+        PAR_FOLD_ADLER();
         if (fallback) {
             // the serial decoder redoes this block (and whatever follows) and owns the result record
             __syncthreads();
@@ -566,6 +627,17 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
             r->resume_bit    = resume_bit;
             r->resume_out    = resume_out;
             r->phase         = phase;
+            if (adler_on && job.format != PNGB200_FORMAT_GZIP) {
+                // LZ77.InflatorBuffers.advance(.checksum): compare with the trailer (InflatorBuffers.swift:109-130)
+                const uint32_t computed = sh.s2 << 16 | sh.s1;
+                r->checksum = computed;
+                r->ck_done  = 1;
+                if (r->trailer_seen && job.format != PNGB200_FORMAT_IOS && r->status >= 0 && r->declared != computed) {
+                    r->status = PNGB200_ERR_STREAM_CHECKSUM;
+                    r->err_a  = r->declared;
+                    r->err_b  = computed;
+                }
+            }
         }
         if (t == 0) {
             for (int k = 0; k < 12; ++k) r->stat_cycles[k] = sh.cyc[k];
@@ -577,10 +649,15 @@ __global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel
     }
 }
 
+__global__ void __launch_bounds__(PAR_THREADS, PAR_CTAS_PER_SM) inflate_parallel_kernel(ParParams P) { inflate_parallel_body(P); }
+__global__ void __launch_bounds__(PAR_THREADS, 3) inflate_parallel_kernel3(ParParams P) { inflate_parallel_body(P); }
+
 #ifndef PNGB200_EMU
 // host side: opt in to the large dynamic shared memory on the current device (once per context)
 inline int configure_inflate_parallel()
 {
+    int rc = (int)cudaFuncSetAttribute(inflate_parallel_kernel3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParShared));
+    if (rc) return rc;
     return (int)cudaFuncSetAttribute(inflate_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(ParShared));
 }
@@ -601,6 +678,7 @@ inline uint64_t par_scratch_stride(uint64_t bitmap_words)
 using par::ParParams;
 using par::ParShared;
 using par::inflate_parallel_kernel;
+using par::inflate_parallel_kernel3;
 using par::PAR_THREADS;
 using par::PAR_CTAS_PER_SM;
 using par::par_bitmap_words;

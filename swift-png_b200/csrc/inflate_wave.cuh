@@ -636,6 +636,16 @@ __device__ __forceinline__ void adler_bytes(const uint8_t* p, uint64_t n, uint64
         bw += (wt - i) * p[i];
     }
 }
+// the same with 32-bit accumulators: enough for one thread's chunks of a wave that fits the shared-memory image
+// (<= 9 chunks x weight <= 32784 x byte sum <= 4080 < 2^31)
+__device__ __forceinline__ void adler_chunk16_u32(uint4 x, uint32_t wt, uint32_t& a, uint32_t& bw)
+{
+    const uint32_t s = __vsadu4(x.x, 0) + __vsadu4(x.y, 0) + __vsadu4(x.z, 0) + __vsadu4(x.w, 0);
+    const uint32_t wsum = __dp4a(x.x, 0x03020100u, 0u) + __dp4a(x.y, 0x07060504u, 0u) +
+                          __dp4a(x.z, 0x0b0a0908u, 0u) + __dp4a(x.w, 0x0f0e0d0cu, 0u);
+    a += s;
+    bw += wt * s - wsum;
+}
 __device__ __forceinline__ void adler_chunk16(uint4 x, uint64_t wt, uint64_t& a, uint64_t& bw)
 {
     const uint32_t s = __vsadu4(x.x, 0) + __vsadu4(x.y, 0) + __vsadu4(x.z, 0) + __vsadu4(x.w, 0);
@@ -1220,24 +1230,24 @@ __global__ void __launch_bounds__(WV_THREADS, WV_CTAS_PER_SM) inflate_wave_kerne
                         const uint32_t rb16  = rbase - shift;                // ring position of gbase
                         const uint32_t end   = shift + total;                // bytes [shift, end) are ours
                         const uint32_t nq    = (end + 15) >> 4;
-                        uint64_t a = 0, bw = 0;
+                        uint32_t a = 0, bw = 0;
                         for (uint32_t c = t; c < nq; c += WV_THREADS) {
                             const uint32_t lo = c << 4, hi = lo + 16;
                             if (lo >= shift && hi <= end) {
                                 const uint4 x = *reinterpret_cast<const uint4*>(sh.ring + ((rb16 + lo) & 0xffffu));
                                 reinterpret_cast<uint4*>(gbase)[c] = x;
-                                adler_chunk16(x, end - lo, a, bw);
+                                adler_chunk16_u32(x, end - lo, a, bw);
                             } else {
                                 for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) {
                                     const uint8_t v = sh.ring[(rb16 + k) & 0xffffu];
                                     gbase[k] = v;
                                     a += v;
-                                    bw += (uint64_t)(end - k) * v;
+                                    bw += (end - k) * v;
                                 }
                             }
                         }
                         if (adler_on) {
-                            uint32_t a32 = (uint32_t)a, b32 = (uint32_t)(bw % ADLER_MOD32);
+                            uint32_t a32 = a, b32 = bw % ADLER_MOD32;
                             for (int o = 16; o; o >>= 1) {
                                 a32 += __shfl_down_sync(0xffffffffu, a32, o);
                                 b32 += __shfl_down_sync(0xffffffffu, b32, o);

@@ -470,7 +470,10 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
                 pp.order = d_order;
                 pp.scratch = ctx->d_scratch.as<uint8_t>();
                 pp.count = (int)par.size();
-                inflate_parallel_kernel<<<grid, PAR_THREADS, sizeof(ParShared), ctx->stream>>>(pp);
+                if (par.size() <= (size_t)ctx->sm_count * 3)
+                    inflate_parallel_kernel3<<<grid, PAR_THREADS, sizeof(ParShared), ctx->stream>>>(pp);
+                else
+                    inflate_parallel_kernel<<<grid, PAR_THREADS, sizeof(ParShared), ctx->stream>>>(pp);
             }
             ctx->launches++;
         }

@@ -210,3 +210,29 @@ def test_block_search_ignores_header_lookalike_in_stored_data(seglib):
     for nseg in (2, 3, 4):
         rc, got, _ = run_segmented(seglib, z2, len(plain), nseg)
         assert rc == 1 or got == plain
+
+
+# ---- the round-1 engine (inflate_parallel_kernel: big batches) under the same emulator ----
+def test_round1_engine_decodes_and_checksums(lib):
+    L = emu.load("emu_inflate_old")
+    L.emu_inflate_parallel.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(emu.Result), C.c_int]
+    rng = np.random.default_rng(13)
+    filt, _ = photo_stream(256, 96)
+    cases = [photo_stream(320, 200)] + [corpus.zlib_png_stream(corpus.make("graphic", 640, 480, 1), 4, 6)]
+    mixed = filt + rng.integers(0, 256, 70_000, dtype=np.uint8).tobytes() + bytes(200_000) + filt
+    cases.append((mixed, zlib.compress(mixed, 6)))
+    for plain, z in cases:
+        for order in (0, 4):
+            src = (C.c_uint8 * (len(z) + 8)).from_buffer_copy(z + b"\0" * 8)
+            out = (C.c_uint8 * (len(plain) + 64))()
+            r = emu.Result()
+            st = L.emu_inflate_parallel(C.addressof(src), len(z), C.addressof(out), len(plain), ZLIB, C.byref(r), order)
+            assert st == 0 and bytes(out)[: r.produced] == plain
+            assert r.ck_done == 1 and r.checksum == zlib.adler32(plain) and r.stat[3] == 0
+    bad = bytearray(cases[0][1])
+    bad[-2] ^= 4                                   # wrong Adler-32 in the trailer
+    src = (C.c_uint8 * (len(bad) + 8)).from_buffer_copy(bytes(bad) + b"\0" * 8)
+    out = (C.c_uint8 * (len(cases[0][0]) + 64))()
+    r = emu.Result()
+    st = L.emu_inflate_parallel(C.addressof(src), len(bad), C.addressof(out), len(cases[0][0]), ZLIB, C.byref(r), 0)
+    assert st == oracle.inflate(bytes(bad), oracle.ZLIB, len(cases[0][0]))[0] != 0
