@@ -145,7 +145,7 @@ int          pngb200_ctx_segment_stats(pngb200_ctx* ctx, uint64_t out[3]);
  * -DDUMP_FILTERED_SCANLINES output (Sources/PNG/Decoding/PNG.Decoder.swift:96-98,128). */
 int          pngb200_ctx_filter_histogram(pngb200_ctx* ctx, uint64_t out[6]);
 /* inflate_mode: 0 automatic; 1 one warp per stream; 2 a whole CTA per stream, never cut; 3 / 4 force the
- * ring-window / the round-1 intra-stream kernel; 5 as 0 */
+ * ring-window / the round-1 intra-stream kernel; 5 as 0; 6 force the cell kernel (inflate_cells.cuh) */
 
 /* ---- batched one-shot entry points (the throughput path) ---- */
 

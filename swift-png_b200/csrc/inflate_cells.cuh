@@ -1,0 +1,732 @@
+// inflate_cells.cuh -- intra-stream parallel DEFLATE inflate, third generation ("cells").
+//
+// Same decomposition as inflate_wave.cuh -- one CTA of 256 threads per stream, WAVES of 256 subsequences x
+// 256 bits staged in shared memory, speculate / walk / chain / count exactly as there -- but the LZ77 half is
+// new.  The ring kernel executed copies token by token (a lane per token, byte loops of very different
+// lengths side by side, a sorted list + an "unresolved" bitmap for copies whose source was not final yet, and a
+// polling sweep whose duration is the depth of the copy -> copy dependency chain: ncu r02 charged 33 % of all
+// warp instructions at 4-9 active lanes and 21 % of the stall samples to that machinery).  Here a wave's output
+// is an array of 16-bit CELLS in shared memory, one per output byte:
+//
+//      0x0000 .. 0x00ff   a final byte
+//      0x0100 .. 0x80ff   "same byte as window position s", s = cell - 0x8100 in [-32768, -1] relative to the
+//                         wave's first output byte (bytes earlier waves have already stored to HBM)
+//      0xc000 .. 0xffff   "same byte as cell j" of this wave, j = cell & 0x3fff, always in front of the cell
+//
+//   E. emit     every thread decodes its share once more and only WRITES cells: a literal is its byte, an LZ77
+//               copy is `run` pointer cells (no source is read, nothing waits, overlapping copies need no
+//               special case: cell p points at p - dist, which is a cell of the same copy).
+//   F. resolve  pointer jumping.  Each thread sweeps a contiguous chunk of cells in ascending order and replaces
+//               every in-wave pointer by the cell it points at.  Within a chunk the sweep has sequential
+//               semantics (the target was already swept), so after round one every surviving pointer leaves its
+//               chunk, and every further round at least halves the number of chunks on a chain: two or three
+//               rounds for PNG data, ceil(log2 256) + 1 at worst.  Racing reads are harmless -- any value a cell
+//               ever holds is a true statement about its byte.  All lanes active, no atomics, no polling.
+//   G. store    cells -> bytes, 16 per thread and step: final cells as they are, window cells gathered from the
+//               stream's own output in HBM/L2 (stored by earlier waves), 16-byte coalesced stores, Adler-32 partial
+//               sums from the same registers.
+//
+// There is no window in shared memory any more (the ring cost 64 KiB per stream): 75 KB per CTA, three CTAs per SM.
+// A wave whose output does not fit the cell array is CUT at the token that would overflow it: the tokens in
+// front are emitted, the next wave starts at that token, and the number of subsequences the next wave
+// speculates on shrinks to what the cut wave used (it grows back by doubling), so highly compressible data costs
+// idle threads, not repeated speculation.  Irregular input (invalid symbol on the chain, truncation, output
+// overflow, a distance reaching in front of the output) goes to the serial decoder as before.
+//
+// Symbolic segment jobs (several CTAs per stream) stay with inflate_wave_kernel.
+//
+// Replaces the reference's serial token loop Stream.readBlock(with:) and InflatorOut.expand
+// (Sources/LZ77/Inflator/LZ77.InflatorBuffers.Stream.swift:266-381, LZ77.InflatorOut.swift:124-140),
+// the window of LZ77.InflatorOut (LZ77.InflatorOut.swift:86-110) and, for zlib streams, the running
+// MRC32 (Sources/LZ77/Wrappers/LZ77.MRC32.swift:26-47).
+#pragma once
+
+#include "inflate_wave.cuh"   // shared pieces: FastBits, wv_decode, wv_fast_header, StagedReader, bulk copy, Adler helpers
+
+namespace pngb200 {
+
+constexpr int      CL_CTAS_PER_SM = 3;
+constexpr uint32_t CL_SLOTS       = 16000;                 // cell slots (16-bit), <= 16384 (14-bit cell index)
+constexpr uint32_t CL_CAP         = CL_SLOTS - 16;         // largest wave output (the first slots mirror dst's 16-byte phase)
+constexpr uint32_t CL_INWAVE      = 0xc000u;               // cell >= this: pointer to cell (cell & 0x3fff)
+constexpr uint32_t CL_WINDOW_BIAS = 0x8100u;               // 0x100 <= cell < 0x8100: window position cell - 0x8100
+constexpr uint32_t CL_MIN_SUBS    = 32;                    // a cut wave never shrinks its successor below one warp
+
+struct ClShared {
+    SerialShared ser;
+    uint32_t     words[WV_SMEM_WORDS];
+    uint32_t     mask[8 * WV_THREADS];          // as in WvShared
+    uint32_t     ck[8 * WV_THREADS];
+    uint32_t     exit_[WV_THREADS];
+    uint32_t     wpos_[WV_THREADS];
+    uint32_t     wn_[WV_THREADS];
+    uint64_t     cross_[WV_THREADS];
+    uint16_t     wc_[WV_THREADS];
+    uint16_t     next_[WV_THREADS];
+    uint8_t      kind_[WV_THREADS];
+    uint8_t      wlist[2][WV_THREADS];
+    uint32_t     wcount[3];
+    uint64_t     warp_sums[WV_WARPS + 1];
+    uint32_t     adler_a[WV_WARPS], adler_b[WV_WARPS];
+    uint32_t     exc[WV_WARPS], valid[WV_WARPS];
+    uint32_t     last, term, anomaly, ticket;
+    uint32_t     cut_pos, cut_out;              // a cut wave: bit position of the first token not emitted, bytes emitted
+    uint64_t     cyc[12], tick;
+    uint64_t     pf_bar;
+    WvHeader     hdr;
+    uint16_t     cells[CL_SLOTS] __align__(32);
+};
+static_assert(sizeof(ClShared) <= (228 * 1024 - CL_CTAS_PER_SM * 1024) / CL_CTAS_PER_SM, "three CTAs per SM");
+static_assert(CL_SLOTS <= 16384 && CL_SLOTS % 16 == 0, "14-bit cell index");
+
+typedef volatile uint16_t* cellp_t;
+
+// the pointer cells of one LZ77 copy: destination slots [j, j + run), first slot of the wave `jbeg`
+__device__ __forceinline__ void cells_copy(cellp_t ch, uint32_t j, uint32_t run, uint32_t dist, uint32_t jbeg)
+{
+    const int32_t  src  = (int32_t)j - (int32_t)dist;                 // slot of the first source byte (may lie in front of the wave)
+    const uint32_t nwin = src >= (int32_t)jbeg ? 0u : min(run, (uint32_t)((int32_t)jbeg - src));
+    // window part: position relative to the wave's first byte = src + k - jbeg, in [-32768, -1]
+    uint32_t code = (uint32_t)((int32_t)CL_WINDOW_BIAS + src - (int32_t)jbeg);
+    uint32_t k = 0;
+    for (; k < nwin; ++k) ch[j + k] = (uint16_t)(code + k);
+    code = CL_INWAVE + (uint32_t)src;                                 // src + k >= jbeg >= 0 from here on
+    for (; k < run; ++k) ch[j + k] = (uint16_t)(code + k);
+}
+
+__global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kernel(WvParams P)
+{
+    PNGB200_DYN_SMEM(cl_smem);
+    ClShared& sh = *reinterpret_cast<ClShared*>(cl_smem);
+    const uint32_t t    = threadIdx.x;
+    const unsigned lane = lane_id(), warp = t >> 5;
+    if (t == 0) mbar_init(&sh.pf_bar, 1);
+    static_assert(offsetof(ClShared, ck) == offsetof(ClShared, mask) + sizeof(uint32_t) * 8 * WV_THREADS, "prefetch area = mask ++ ck");
+    static_assert(offsetof(ClShared, mask) % 16 == 0 && offsetof(ClShared, cells) % 32 == 0, "alignment");
+    uint32_t pf_parity = 0;
+    const saddr_t words_addr = smem_addr(sh.words);
+    const saddr_t lit = smem_addr(sh.ser.lit), dstt = smem_addr(sh.ser.dist);
+    uint32_t* const mk = sh.mask;
+    cellp_t const ch = sh.cells;
+
+    for (;;) {
+        __syncthreads();
+        if (t == 0) {
+            sh.ticket = atomicAdd(P.ticket, 1u);
+            sh.anomaly = 0;
+            for (int k = 0; k < 12; ++k) sh.cyc[k] = 0;
+            sh.tick = (uint64_t)clock64();
+        }
+        __syncthreads();
+        if (sh.ticket >= (uint32_t)P.count) return;
+        const int       j   = P.order ? (int)P.order[sh.ticket] : (int)sh.ticket;
+        const StreamJob job = P.jobs[j];
+        StreamResult*   r   = P.results + j;
+
+        BitReader br;
+        br.init(job.src, job.src_len, job.start_bit);
+        uint64_t out    = job.start_out;
+        uint32_t blocks = 0, waves = 0, sweep_rounds = 0, cuts = 0;
+        uint64_t n_tokens = 0, n_matches = 0, walk_tokens = 0;
+        int      st     = PNGB200_OK;
+        uint32_t phase  = (uint32_t)job.phase;
+        uint64_t resume_bit = job.start_bit, resume_out = job.start_out;
+        uint8_t* const dst = job.dst;
+        bool fallback = false;
+        bool     pf_pending = false;
+        uint64_t pf_first = 0;
+        uint32_t nsub = WV_THREADS;             // subsequences the next wave speculates on
+        const bool adler_on = job.start_out == 0;
+        uint32_t   s1 = 1, s2 = 0;
+        uint64_t   pend_len = 0;
+        bool       pend = false;
+        auto fold_adler = [&]() {
+            if (pend && t == 0) {
+                uint64_t A = 0, B = 0;
+                for (int w = 0; w < WV_WARPS; ++w) { A += sh.adler_a[w]; B += sh.adler_b[w]; }
+                s2 = (uint32_t)((s2 + (pend_len % ADLER_MOD32) * s1 + B) % ADLER_MOD32);
+                s1 = (uint32_t)((s1 + A) % ADLER_MOD32);
+            }
+            pend = false;
+        };
+        auto adler_hbm = [&](const uint8_t* p, uint64_t n) {
+            uint64_t a = 0, bw = 0;
+            const uint64_t per = (n + WV_THREADS - 1) / WV_THREADS;
+            const uint64_t lo = min((uint64_t)t * per, n), hi = min(lo + per, n);
+            adler_bytes(p + lo, hi - lo, n - lo, a, bw);
+            uint32_t a32 = (uint32_t)(a % ADLER_MOD32), b32 = (uint32_t)(bw % ADLER_MOD32);
+            for (int o = 16; o; o >>= 1) {
+                a32 += __shfl_down_sync(0xffffffffu, a32, o);
+                b32 += __shfl_down_sync(0xffffffffu, b32, o);
+            }
+            if (lane == 0) { sh.adler_a[warp] = a32; sh.adler_b[warp] = b32; }
+            pend = true;
+            pend_len = n;
+        };
+        auto tick = [&](int i) {
+            if (t == 0) {
+                const uint64_t now = (uint64_t)clock64();
+                sh.cyc[i] += now - sh.tick;
+                sh.tick = now;
+            }
+        };
+
+        if (phase == 0) {
+            st = read_stream_header(br, job.format, r);
+            if (st == PNGB200_OK) {
+                resume_bit = br.at();
+                phase = 1;
+            }
+        }
+        if (st == PNGB200_OK && phase == 2) st = read_trailer(br, job.format, r);
+
+        while (st == PNGB200_OK && phase == 1) {
+            __syncthreads();
+            fold_adler();
+            {
+                const uint64_t hbase = br.pos >> 5;
+                for (uint32_t k = t; k < WV_HDR_WORDS; k += WV_THREADS) sh.words[k] = br.load_word(hbase + k);
+                __syncthreads();
+                if (warp == 0) {
+                    WvHeader h;
+                    if (!wv_fast_header(sh, hbase << 5, br.pos, br.total_bits, (int)lane, h)) {
+                        int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
+                        uint32_t stored0 = 0;
+                        StagedReader sr;
+                        sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
+                        int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
+                        h = WvHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                    }
+                    if (lane == 0) sh.hdr = h;
+                }
+            }
+            __syncthreads();
+            const WvHeader hdr = sh.hdr;
+            st = hdr.status;
+            if (st != PNGB200_OK) break;
+            const int      type = hdr.type, final = hdr.final;
+            const uint32_t stored = hdr.stored;
+            br.seek(hdr.pos);
+            if (type != 0) {
+                st = build_block_tables(&sh.ser, r, hdr.nlit, hdr.ndist, (int)t, WV_THREADS);
+                if (st != PNGB200_OK) break;
+            }
+            tick(0);
+            if (type == 0) {
+                if (!br.have(8 * (uint64_t)stored)) { st = PNGB200_NEED_MORE_INPUT; break; }
+                if (out + stored > job.dst_cap) { st = fail(r, PNGB200_ERR_OUTPUT_CAPACITY); break; }
+                const uint8_t* s = job.src + (br.at() >> 3);
+                for (uint32_t k = t; k < stored; k += WV_THREADS) dst[out + k] = s[k];
+                if (adler_on && stored) adler_hbm(s, stored);
+                out += stored;
+                br.seek(br.pos + 8 * (uint64_t)stored);
+                __syncthreads();
+                fold_adler();
+                tick(9);
+            } else {
+                bool block_done = false;
+                while (!block_done) {
+                    ++waves;
+                    const uint32_t wave_bits = nsub * WV_SUB_BITS;
+                    // ---- stage the wave's bits in shared memory ----
+                    const uint64_t wstart = br.pos;
+                    const uint64_t wbase  = (wstart >> 5) & ~(uint64_t)7;
+                    __syncthreads();
+                    bool staged = false;
+                    if (pf_pending) {
+                        while (!mbar_try_wait(&sh.pf_bar, pf_parity)) {}
+                        pf_parity ^= 1;
+                        pf_pending = false;
+                        if (wbase >= pf_first && wbase - pf_first < 4) {
+                            const uint32_t* lin = sh.mask + (uint32_t)(wbase - pf_first);
+                            for (uint32_t k = t; k < WV_WORDS; k += WV_THREADS) sh.words[k + (k >> 3)] = lin[k];
+                            staged = true;
+                        }
+                    }
+                    if (!staged)
+                        for (uint32_t k = t; k < WV_WORDS; k += WV_THREADS)
+                            sh.words[k + (k >> 3)] = br.load_word(wbase + k);
+                    if (t == 0) {
+                        sh.wcount[0] = 0;
+                        sh.cut_pos = 0xffffffffu;
+                    }
+                    __syncthreads();                                      // (1)
+                    fold_adler();
+                    tick(1);
+                    const uint32_t rel0  = (uint32_t)(wstart - (wbase << 5));  // < 256
+                    const uint32_t base  = t * WV_SUB_BITS;
+                    const uint32_t limit = base + WV_SUB_BITS;
+
+                    // ---- A. speculative decode of my subsequence: token-start map, checkpoints, totals ----
+                    uint32_t nout = 0, ncopy = 0, flags = 0, exit_bit = base;
+                    {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) mk[k * WV_THREADS + t] = 0;
+                        sh.ck[t] = 0;
+                        uint32_t n = 0;
+                        if (t < nsub) {
+                            FastBits b;
+                            b.init(words_addr, t == 0 ? rel0 : base);
+                            uint32_t mi = 0, mw = 0;
+                            while (b.pos < limit) {
+                                const uint32_t rr = b.pos - base, wi = rr >> 5;
+                                if (wi != mi) {
+                                    mk[mi * WV_THREADS + t] = mw;
+                                    mw = 0;
+                                    mi = wi;
+                                    sh.ck[wi * WV_THREADS + t] = nout | ncopy << 16;
+                                }
+                                mw |= 1u << (rr & 31);
+                                uint32_t run = 0, dist = 0, cp = 0;
+                                const uint32_t s = wv_decode<false>(b, lit, dstt, run, dist, cp);
+                                if (s) { flags = s; break; }
+                                nout += cp ? run : 1u;
+                                ncopy += cp;
+                                ++n;
+                            }
+                            mk[mi * WV_THREADS + t] = mw;
+                            exit_bit = b.pos;
+                        } else {
+                            flags = PF_BAD;       // not part of this wave: never reached by the chain
+                        }
+                        WV_COUNT(0, n);
+                    }
+                    sh.exit_[t] = exit_bit;
+                    sh.cross_[t] = 0;
+                    __syncthreads();                                      // (2) maps complete
+                    tick(2);
+
+                    // ---- B. walks (as in inflate_wave_kernel) ----
+                    {
+                        uint32_t u = t, pos = exit_bit, wn = 0, wc = 0;
+                        bool     active = flags == 0;
+                        if (!active) {
+                            sh.kind_[t] = (uint8_t)(flags == PF_EOB ? WK_OWN_EOB : WK_OWN_BAD);
+                            sh.wpos_[t] = exit_bit;
+                            sh.wn_[t] = 0;
+                            sh.wc_[t] = 0;
+                        }
+                        for (uint32_t round = 0;; ++round) {
+                            const uint32_t K = WV_WALK_K << min(round, 6u);
+                            bool     still = false;
+                            uint32_t iters = 0;
+                            if (active) {
+                                FastBits b;
+                                b.init(words_addr, pos);
+                                uint32_t kind = WK_RUNNING;
+                                const uint32_t first_sub = sh.exit_[u] >> 8;
+                                bool     crossed = sh.cross_[u] != 0;
+                                for (; iters < K; ++iters) {
+                                    const uint32_t p = b.pos;
+                                    if (p >= wave_bits) { kind = WK_END; break; }
+                                    const uint32_t s = p >> 8, rr = p & 255u;
+                                    if (!crossed && s > first_sub) {
+                                        sh.cross_[u] = 1ull << 63 | (uint64_t)p << 40 | (uint64_t)(wc & 0xffu) << 24 | (wn & 0xffffffu);
+                                        crossed = true;
+                                    }
+                                    if ((mk[(rr >> 5) * WV_THREADS + s] >> (rr & 31)) & 1u) { kind = WK_SYNC; break; }
+                                    uint32_t run = 0, dist = 0, cp = 0;
+                                    const uint32_t e = wv_decode<false>(b, lit, dstt, run, dist, cp);
+                                    if (e) { kind = e == PF_EOB ? WK_EOB : WK_BAD; break; }
+                                    wn += cp ? run : 1u;
+                                    wc += cp;
+                                }
+                                sh.wpos_[u] = b.pos;
+                                sh.wn_[u]   = wn;
+                                sh.wc_[u]   = (uint16_t)wc;
+                                sh.kind_[u] = (uint8_t)kind;
+                                still = kind == WK_RUNNING;
+                                walk_tokens += iters;
+                            }
+                            WV_COUNT(1, iters);
+                            if (t == 0) sh.wcount[(round + 1) % 3] = 0;
+                            const unsigned bal = __ballot_sync(0xffffffffu, still);
+                            if (still) {
+                                uint32_t at = 0;
+                                const int leader = __ffs((int)bal) - 1;
+                                if ((int)lane == leader) at = atomicAdd(&sh.wcount[round % 3], (uint32_t)__popc(bal));
+                                at = __shfl_sync(bal, at, leader);
+                                sh.wlist[round & 1][at + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)u;
+                            }
+                            __syncthreads();
+                            const uint32_t cnt = sh.wcount[round % 3];
+                            if (cnt == 0) break;
+                            active = t < cnt;
+                            if (active) {
+                                u   = sh.wlist[round & 1][t];
+                                pos = sh.wpos_[u];
+                                wn  = sh.wn_[u];
+                                wc  = sh.wc_[u];
+                            }
+                        }
+                    }
+                    tick(3);
+                    const uint32_t kind = sh.kind_[t], wpos = sh.wpos_[t];
+                    {
+                        const bool joins_next = kind == WK_SYNC && (wpos >> 8) == t + 1;
+                        sh.next_[t] = (uint16_t)(kind == WK_SYNC ? wpos >> 8 : 0xffffu);
+                        const unsigned e = __ballot_sync(0xffffffffu, !joins_next);
+                        if (lane == 0) sh.exc[warp] = e;
+                    }
+                    __syncthreads();                                      // (3)
+
+                    // ---- C. the true chain: orbit of thread 0 ----
+                    if (t == 0) {
+                        uint32_t E[WV_WARPS];
+#pragma unroll
+                        for (int w = 0; w < WV_WARPS; ++w) E[w] = sh.exc[w];
+                        uint32_t cur = 0, x = 0;
+                        bool     done = false;
+#pragma unroll
+                        for (int w = 0; w < WV_WARPS; ++w) {
+                            uint32_t v = 0;
+                            while (!done && cur < 32u * (w + 1)) {
+                                const uint32_t lo = cur - 32u * w;
+                                const uint32_t m = E[w] & (~0u << lo);
+                                if (m == 0) {
+                                    v |= ~0u << lo;
+                                    cur = 32u * (w + 1);
+                                    break;
+                                }
+                                const uint32_t b = (uint32_t)__ffs((int)m) - 1;
+                                x = 32u * w + b;
+                                v |= bit_mask(lo, b + 1);
+                                const uint32_t nx = sh.next_[x];
+                                if (nx == 0xffffu) done = true;
+                                else cur = nx;
+                            }
+                            sh.valid[w] = v;
+                        }
+                        sh.last = x;
+                        sh.term = sh.kind_[x];
+                    }
+                    __syncthreads();                                      // (4)
+                    tick(4);
+
+                    // ---- D. my share of the chain ----
+                    const bool     on_chain = (sh.valid[warp] >> lane) & 1u;
+                    const uint32_t last = sh.last, term = sh.term;
+                    uint32_t from = rel0, to = exit_bit;
+                    uint32_t my_nout = 0, my_ncopy = 0;
+                    bool     adopted = false;
+                    if (on_chain) {
+                        uint32_t pn = 0, pc = 0, pre_n = 0, pre_c = 0;
+                        if (t > 0) {
+                            uint32_t w = warp, m = sh.valid[w] & ((1u << lane) - 1u);
+                            while (m == 0) m = sh.valid[--w];
+                            const uint32_t pred = w * 32 + 31 - (uint32_t)__clz((int)m);
+                            const uint32_t p0 = sh.wpos_[pred];
+                            from = sh.exit_[pred];
+                            pn = sh.wn_[pred];
+                            pc = sh.wc_[pred];
+                            if (pred + 1 < t) {
+                                const uint64_t cr = sh.cross_[pred];
+                                if (cr) {
+                                    from = (uint32_t)(cr >> 40) & 0x1ffffu;
+                                    pn -= (uint32_t)cr & 0xffffffu;
+                                    pc -= (uint32_t)(cr >> 24) & 0xffu;
+                                }
+                            }
+                            const uint32_t rr = p0 - base, q = rr >> 5;
+                            const uint32_t ck = sh.ck[q * WV_THREADS + t];
+                            pre_n = ck & 0xffffu;
+                            pre_c = ck >> 16;
+                            const uint32_t first = (uint32_t)__ffs((int)mk[q * WV_THREADS + t]) - 1;
+                            if (first != (rr & 31)) {
+                                FastBits b;
+                                b.init(words_addr, base + 32 * q + first);
+                                while (b.pos != p0 && b.pos < limit) {
+                                    uint32_t run = 0, dist = 0, cp = 0;
+                                    if (wv_decode<false>(b, lit, dstt, run, dist, cp)) break;
+                                    pre_n += cp ? run : 1u;
+                                    pre_c += cp;
+                                }
+                            }
+                        }
+                        my_nout  = pn + nout - pre_n;
+                        my_ncopy = pc + ncopy - pre_c;
+                        if (t == last) {
+                            to = wpos;
+                            my_nout += sh.wn_[t];
+                            my_ncopy += sh.wc_[t];
+                            if (term == WK_BAD || term == WK_OWN_BAD || (wbase << 5) + wpos > br.total_bits)
+                                sh.anomaly = 1;
+                        }
+                    }
+                    else if (t > 0 && ((sh.valid[(t - 1) >> 5] >> ((t - 1) & 31)) & 1u) && sh.kind_[t - 1] == WK_SYNC) {
+                        const uint64_t cr = sh.cross_[t - 1];
+                        if (cr) {
+                            adopted  = true;
+                            from     = sh.exit_[t - 1];
+                            to       = (uint32_t)(cr >> 40) & 0x1ffffu;
+                            my_nout  = (uint32_t)cr & 0xffffffu;
+                            my_ncopy = (uint32_t)(cr >> 24) & 0xffu;
+                        }
+                    }
+                    const uint64_t mine = (uint64_t)my_ncopy << 40 | my_nout;
+                    uint64_t incl = mine;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        uint64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += v;
+                    }
+                    if (lane == 31) sh.warp_sums[warp] = incl;
+                    __syncthreads();                                      // (5)
+                    if (warp == 0) {
+                        uint64_t ws = lane < WV_WARPS ? sh.warp_sums[lane] : 0, wi = ws;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            uint64_t v = __shfl_up_sync(0xffffffffu, wi, o);
+                            if ((int)lane >= o) wi += v;
+                        }
+                        if (lane < WV_WARPS) sh.warp_sums[lane] = wi - ws;
+                        if (lane == WV_WARPS - 1) sh.warp_sums[WV_WARPS] = wi;
+                    }
+                    __syncthreads();                                      // (6)
+                    tick(5);
+                    const uint64_t excl    = sh.warp_sums[warp] + incl - mine;
+                    const uint64_t o64     = excl & 0xffffffffffull;
+                    const uint64_t total64 = sh.warp_sums[WV_WARPS] & 0xffffffffffull;
+                    const uint32_t np      = (uint32_t)(sh.warp_sums[WV_WARPS] >> 40);
+                    const bool     cut     = total64 > CL_CAP;            // the wave is cut at the token that would overflow the cells
+                    if (sh.anomaly || out + total64 > job.dst_cap) {
+                        fallback = true;
+                        break;
+                    }
+                    // ---- prefetch of the next wave's words (predicted start; a cut wave misses and stages directly) ----
+                    if (!cut) {
+                        const uint64_t nbase = wbase + wave_bits / 32;
+                        const uint64_t first = nbase - ((((uintptr_t)br.words >> 2) + nbase) & 3);
+                        if (first >= 1 && (first + WV_PF_WORDS + 1) * 32 <= br.total_bits) {
+                            if (t == 0) {
+                                fence_proxy_async();
+                                mbar_expect_tx(&sh.pf_bar, sizeof(uint32_t) * WV_PF_WORDS);
+                                bulk_g2s(sh.mask, br.words + first, sizeof(uint32_t) * WV_PF_WORDS, &sh.pf_bar);
+                            }
+                            pf_pending = true;
+                            pf_first = first;
+                        }
+                    }
+                    // ---- E. emit: decode my share once more, write cells ----
+                    uint8_t* const wdst  = dst + out;                        // HBM address of wave offset 0
+                    const uint32_t shift = (uint32_t)((uintptr_t)wdst & 15); // slot of wave offset 0 (dst's 16-byte phase)
+                    const uint32_t reach = out >= WV_WINDOW ? 0x7fffffffu : (uint32_t)out;
+                    uint32_t emitted = 0, my_stop = 0xffffffffu, o = 0;
+                    if ((on_chain || adopted) && from != to) {
+                        if (o64 >= CL_CAP) {
+                            my_stop = from;                  // nothing of my share fits
+                            o = CL_CAP;                      // (if I am the first such thread, the shares in front end exactly here)
+                        } else {
+                            o = (uint32_t)o64;
+                            bool bad_ref = false;
+                            FastBits b;
+                            b.init(words_addr, from);
+                            while (b.pos != to && b.pos < wave_bits + 64) {
+                                const uint32_t tok = b.pos;
+                                uint32_t run = 0, dist = 0, cp = 0;
+                                if (wv_decode<true>(b, lit, dstt, run, dist, cp)) break;
+                                const uint32_t n = cp ? run : 1u;
+                                if (o + n > CL_CAP) { my_stop = tok; break; }
+                                if (!cp) ch[shift + o] = (uint16_t)run;
+                                else if (dist > reach + o) { bad_ref = true; break; }   // invalidStringReference: the serial decoder reports it
+                                else cells_copy(ch, shift + o, run, dist, shift);
+                                o += n;
+                                ++emitted;
+                            }
+                            if (bad_ref) sh.anomaly = 1;
+                        }
+                    }
+                    WV_COUNT(2, emitted);
+                    if (cut && my_stop != 0xffffffffu) atomicMin(&sh.cut_pos, my_stop);
+                    __syncthreads();                                      // (7) cells written
+                    tick(6);
+                    if (sh.anomaly) {
+                        fallback = true;
+                        break;
+                    }
+                    uint32_t total = (uint32_t)total64;
+                    if (cut) {
+                        if (my_stop == sh.cut_pos) sh.cut_out = o;    // exactly one thread stopped there
+                        __syncthreads();
+                        total = sh.cut_out;
+                        ++cuts;
+                    }
+                    // ---- F. resolve: pointer jumping over contiguous chunks, ascending ----
+                    {
+                        const uint32_t jbeg = shift, jend = shift + total;
+                        const uint32_t wlo = jbeg >> 1, whi = (jend + 1) >> 1;
+                        const uint32_t per = ((whi - wlo + WV_THREADS - 1) / WV_THREADS) | 1u;   // odd word stride: no bank conflicts
+                        const uint32_t a = min(wlo + t * per, whi), e = min(a + per, whi);
+                        volatile uint32_t* const cw = reinterpret_cast<volatile uint32_t*>(sh.cells);
+                        uint32_t rounds = 0;
+                        for (;;) {
+                            bool more = false;
+                            for (uint32_t i = a; i < e; ++i) {
+                                const uint32_t w = cw[i];
+                                uint32_t c0 = w & 0xffffu, c1 = w >> 16;
+                                const bool p0 = c0 >= CL_INWAVE && 2 * i >= jbeg;
+                                const bool p1 = c1 >= CL_INWAVE && 2 * i + 1 < jend;
+                                if (p0) {
+                                    c0 = ch[c0 & 0x3fffu];
+                                    ch[2 * i] = (uint16_t)c0;
+                                    more |= c0 >= CL_INWAVE;
+                                }
+                                if (p1) {
+                                    const uint32_t j1 = c1 & 0x3fffu;
+                                    c1 = j1 == 2 * i ? c0 : ch[j1];
+                                    ch[2 * i + 1] = (uint16_t)c1;
+                                    more |= c1 >= CL_INWAVE;
+                                }
+                            }
+                            ++rounds;
+                            if (!__syncthreads_or(more)) break;
+                        }
+                        sweep_rounds += rounds;
+                        WV_COUNT(4, rounds);
+                    }
+                    tick(7);
+                    // ---- G. store: cells -> bytes (window cells gathered from the stream's own output), 16-byte coalesced ----
+                    if (total) {
+                        uint8_t* const gbase = wdst - shift;                 // 16-byte aligned
+                        const uint32_t end   = shift + total;                // slots [shift, end) are ours
+                        const uint32_t nq    = (end + 15) >> 4;
+                        uint32_t a = 0, bw = 0;
+                        auto cell_byte = [&](uint32_t c) -> uint32_t {
+                            // a window cell: relative position c - 0x8100 in [-32768, -1]
+                            return c < 256u ? c : (uint32_t)wdst[(int32_t)c - (int32_t)CL_WINDOW_BIAS];
+                        };
+                        for (uint32_t c = t; c < nq; c += WV_THREADS) {
+                            const uint32_t lo = c << 4, hi = lo + 16;
+                            if (lo >= shift && hi <= end) {
+                                const uint4 h0 = *reinterpret_cast<const uint4*>(sh.cells + lo);
+                                const uint4 h1 = *reinterpret_cast<const uint4*>(sh.cells + lo + 8);
+                                const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                                uint32_t by[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint32_t b0 = cell_byte(hw[2 * q] & 0xffffu), b1 = cell_byte(hw[2 * q] >> 16);
+                                    const uint32_t b2 = cell_byte(hw[2 * q + 1] & 0xffffu), b3 = cell_byte(hw[2 * q + 1] >> 16);
+                                    by[q] = b0 | b1 << 8 | b2 << 16 | b3 << 24;
+                                }
+                                const uint4 x = make_uint4(by[0], by[1], by[2], by[3]);
+                                reinterpret_cast<uint4*>(gbase)[c] = x;
+                                adler_chunk16_u32(x, end - lo, a, bw);
+                            } else {
+                                for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) {
+                                    const uint32_t v = cell_byte(sh.cells[k]);
+                                    gbase[k] = (uint8_t)v;
+                                    a += v;
+                                    bw += (end - k) * v;
+                                }
+                            }
+                        }
+                        if (adler_on) {
+                            uint32_t a32 = a, b32 = bw % ADLER_MOD32;
+                            for (int o2 = 16; o2; o2 >>= 1) {
+                                a32 += __shfl_down_sync(0xffffffffu, a32, o2);
+                                b32 += __shfl_down_sync(0xffffffffu, b32, o2);
+                            }
+                            if (lane == 0) { sh.adler_a[warp] = a32; sh.adler_b[warp] = b32; }
+                            pend = true;
+                            pend_len = total;
+                        }
+                    }
+                    tick(8);
+                    out += total;
+                    if (t == 0) n_matches += np;
+                    n_tokens += emitted;
+                    if (cut) {
+                        // the next wave starts at the first token that did not fit and speculates on as many
+                        // subsequences as this one got through (+ a quarter), at least one warp's worth
+                        const uint32_t cp = sh.cut_pos;
+                        const uint32_t used = (cp >> 8) + 1;
+                        nsub = min((uint32_t)WV_THREADS, max(CL_MIN_SUBS, used + (used >> 2) + 8u));
+                        br.seek((wbase << 5) + cp);
+                    } else {
+                        nsub = min((uint32_t)WV_THREADS, nsub * 2);
+                        br.seek((wbase << 5) + sh.wpos_[last]);
+                        if (term == WK_EOB || term == WK_OWN_EOB) block_done = true;
+                    }
+                }
+                if (fallback) break;
+            }
+            ++blocks;
+            resume_bit = br.at();
+            resume_out = out;
+            if (final) {
+                phase = 2;
+                st = read_trailer(br, job.format, r);
+                break;
+            }
+        }
+        if (pf_pending) {
+            while (!mbar_try_wait(&sh.pf_bar, pf_parity)) {}
+            pf_parity ^= 1;
+            pf_pending = false;
+        }
+        __syncthreads();
+        fold_adler();
+        {
+            uint64_t v0 = n_tokens, v2 = walk_tokens;
+            uint32_t v3 = sweep_rounds;
+            for (int o = 16; o; o >>= 1) {
+                v0 += __shfl_down_sync(0xffffffffu, v0, o);
+                v2 += __shfl_down_sync(0xffffffffu, v2, o);
+                v3 = max(v3, __shfl_down_sync(0xffffffffu, v3, o));
+            }
+            if (lane == 0) {
+                sh.warp_sums[warp] = v0;
+                sh.adler_b[warp] = (uint32_t)min(v2, (uint64_t)0xffffffffu);
+                sh.exc[warp] = v3;
+            }
+            __syncthreads();
+            if (t == 0) {
+                uint64_t tk = 0, wt = 0;
+                uint32_t rr = 0;
+                for (int w = 0; w < WV_WARPS; ++w) {
+                    tk += sh.warp_sums[w];
+                    wt += sh.adler_b[w];
+                    rr = max(rr, sh.exc[w]);
+                }
+                r->stat_waves          = waves;
+                r->stat_sync_rounds    = (uint32_t)min(wt, (uint64_t)0xffffffffu);   // tokens decoded by walks
+                r->stat_resolve_rounds = rr;                                          // pointer-jumping rounds
+                r->stat_tokens         = tk;
+                r->stat_matches        = n_matches;
+                r->stat_deferred       = cuts;                                        // waves cut at the cell capacity
+                for (int k = 0; k < 12; ++k) r->stat_cycles[k] = sh.cyc[k];
+            }
+        }
+        if (fallback) {
+            __syncthreads();
+            if (warp == 0) serial_inflate(sh.ser, job, r, resume_bit, resume_out, 1, blocks);
+        } else if (t == 0) {
+            if (r->status == 0) r->status = st;
+            r->produced      = out;
+            r->consumed_bits = br.at();
+            r->blocks        = blocks;
+            r->resume_bit    = resume_bit;
+            r->resume_out    = resume_out;
+            r->phase         = phase;
+            if (adler_on && job.format != PNGB200_FORMAT_GZIP) {
+                const uint32_t computed = s2 << 16 | s1;
+                r->checksum = computed;
+                r->ck_done  = 1;
+                if (r->trailer_seen && job.format != PNGB200_FORMAT_IOS && r->status >= 0 && r->declared != computed) {
+                    r->status = PNGB200_ERR_STREAM_CHECKSUM;
+                    r->err_a  = r->declared;
+                    r->err_b  = computed;
+                }
+            }
+        }
+        if (t == 0) r->stat_fallback = fallback ? 1u : 0u;
+    }
+}
+
+#ifndef PNGB200_EMU
+inline int configure_inflate_cells()
+{
+    return (int)cudaFuncSetAttribute(inflate_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(ClShared));
+}
+#endif
+
+}  // namespace pngb200

@@ -22,6 +22,7 @@
 #include "crc32.cuh"
 #include "inflate_wave.cuh"
 #include "inflate_parallel.cuh"
+#include "inflate_cells.cuh"
 #include "block_search.cuh"
 #include "inflate_segments.cuh"
 #include "inflate_serial.cuh"
@@ -95,6 +96,7 @@ struct pngb200_ctx {
     cudaStream_t stream = nullptr;
     uint64_t     launches = 0;
     int          inflate_mode = 0;
+    bool         cells_auto = false;     // automatic mode may pick inflate_cells_kernel (set once measured faster)
     int          sm_count = 148;
     std::string  error;
     bool         pending = false;
@@ -428,13 +430,28 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             //  * inflate_parallel_kernel (round 1): 16 KiB output image, window read back from HBM/L2, 4 CTAs per
             //    SM.  Slower per stream, but twice the streams in flight hide its barrier phases: measured r02 on
             //    8K RGBA8 1.96 ms per image against 2.51 ms once a batch exceeds the wave kernel's slots.
+            //  * inflate_cells_kernel (round 2, second half): the same waves, but the LZ77 half works on 16-bit cells in
+            //    shared memory resolved by pointer jumping; no window in shared memory, 3 CTAs per SM.  Waves that
+            //    expand beyond ~16 KB are cut, so it is meant for streams that expand less than ~2x per wave
+            //    (photographic PNG data); flat graphics stay with the ring kernel.
             const size_t wave_slots = (size_t)ctx->sm_count * WV_CTAS_PER_SM;
-            bool use_wave = std::max(par.size(), ctx->peer_streams) <= wave_slots;   // (lanes: the chunks of a host batch run side by side)
-            if (ctx->inflate_mode == 3) use_wave = true;
-            if (ctx->inflate_mode == 4) use_wave = false;
-            const uint64_t bitmap_words = use_wave ? wv_bitmap_words(max_cap) : par_bitmap_words(max_cap);
-            const uint64_t stride = use_wave ? wv_scratch_stride(bitmap_words) : par_scratch_stride(bitmap_words);
-            unsigned grid = (unsigned)std::min<size_t>(par.size(), use_wave ? wave_slots : (size_t)ctx->sm_count * PAR_CTAS_PER_SM);
+            const size_t streams_in_flight = std::max(par.size(), ctx->peer_streams);   // (lanes: the chunks of a host batch run side by side)
+            enum { ENG_PARALLEL = 0, ENG_WAVE = 1, ENG_CELLS = 2 };
+            int engine = streams_in_flight <= wave_slots ? ENG_WAVE : ENG_PARALLEL;
+            if (ctx->inflate_mode == 0 || ctx->inflate_mode == 5) {
+                uint64_t in_bytes = 0, out_bytes = 0;
+                for (uint32_t i : par) { in_bytes += h_jobs[i].src_len; out_bytes += h_jobs[i].dst_cap; }
+                if (ctx->cells_auto && out_bytes <= in_bytes * 9 / 4) engine = ENG_CELLS;
+            }
+            if (ctx->inflate_mode == 3) engine = ENG_WAVE;
+            if (ctx->inflate_mode == 4) engine = ENG_PARALLEL;
+            if (ctx->inflate_mode == 6) engine = ENG_CELLS;
+            const bool use_wave = engine == ENG_WAVE;
+            const uint64_t bitmap_words = engine == ENG_CELLS ? 8 : use_wave ? wv_bitmap_words(max_cap) : par_bitmap_words(max_cap);
+            const uint64_t stride = engine == ENG_CELLS ? 256 : use_wave ? wv_scratch_stride(bitmap_words) : par_scratch_stride(bitmap_words);
+            unsigned grid = (unsigned)std::min<size_t>(par.size(), engine == ENG_CELLS ? (size_t)ctx->sm_count * CL_CTAS_PER_SM
+                                                                   : use_wave         ? wave_slots
+                                                                                      : (size_t)ctx->sm_count * PAR_CTAS_PER_SM);
             size_t need = (size_t)stride * grid + 256;
             // The per-CTA "unresolved" bitmaps must be all-zero when a launch starts; the kernels
             // leave them clean.  A different stride moves the bitmaps onto bytes that held copy
@@ -449,7 +466,15 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             if (!hooked)
                 if (int rc = before_first_launch()) return rc;
             hooked = true;
-            if (use_wave) {
+            if (engine == ENG_CELLS) {
+                WvParams pp{};
+                pp.ticket = ticket;
+                pp.jobs = d_jobs;
+                pp.results = d_results;
+                pp.order = d_order;
+                pp.count = (int)par.size();
+                inflate_cells_kernel<<<grid, WV_THREADS, sizeof(ClShared), ctx->stream>>>(pp);
+            } else if (use_wave) {
                 WvParams pp;
                 pp.bitmap_words = bitmap_words;
                 pp.scratch_stride = stride;
@@ -701,6 +726,7 @@ int run_over_lanes(pngb200_ctx* ctx, size_t count, int memspace, BytesOf bytes_o
         workers.emplace_back([&, l]() {
             pngb200_ctx* lane = ctx->lanes[l];
             lane->inflate_mode = ctx->inflate_mode;
+            lane->cells_auto = ctx->cells_auto;
             lane->parallel_threshold = ctx->parallel_threshold;
             lane->peer_streams = count;
             for (size_t c = l; c < nchunks; c += kLanes) {
@@ -778,6 +804,11 @@ pngb200_ctx* pngb200_ctx_create(int device)
     }
     if (configure_inflate_wave() != 0) {
         set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(WvShared));
+        delete ctx;
+        return nullptr;
+    }
+    if (configure_inflate_cells() != 0) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(ClShared));
         delete ctx;
         return nullptr;
     }
