@@ -45,23 +45,37 @@
 
 namespace pngb200 {
 
-constexpr int      CL_CTAS_PER_SM = 3;
-constexpr uint32_t CL_SLOTS       = 16000;                 // cell slots (16-bit), <= 16384 (14-bit cell index)
+#ifndef CL_CTAS
+#define CL_CTAS 3
+#endif
+#ifndef CL_NSLOTS
+#define CL_NSLOTS 16000
+#endif
+constexpr int      CL_CTAS_PER_SM = CL_CTAS;
+constexpr uint32_t CL_SLOTS       = CL_NSLOTS;             // cell slots (16-bit), <= 16384 (14-bit cell index)
 constexpr uint32_t CL_CAP         = CL_SLOTS - 16;         // largest wave output (the first slots mirror dst's 16-byte phase)
 constexpr uint32_t CL_INWAVE      = 0xc000u;               // cell >= this: pointer to cell (cell & 0x3fff)
 constexpr uint32_t CL_WINDOW_BIAS = 0x8100u;               // 0x100 <= cell < 0x8100: window position cell - 0x8100
 constexpr uint32_t CL_MIN_SUBS    = 32;                    // a cut wave never shrinks its successor below one warp
+// Token staging: the speculative decode (phase A) and the walks (phase B) leave every token they decode in a per-CTA
+// scratch area in global memory (L2 resident: written and read back within one wave), 32 bits per token (run << 16 | distance, or byte << 16), so that the emit
+// phase does not decode a third time -- it reads its share back.  own[t][k]: k-th token thread t decoded in its
+// subsequence; walk[u][k]: k-th token of the walk that started at thread u's exit.
+constexpr uint32_t CL_TCAP        = 64;                    // tokens kept per subsequence (more: the thread decodes again in emit)
+constexpr uint32_t CL_WCAP        = 64;                    // tokens kept per walk
+constexpr uint64_t CL_SCRATCH     = (uint64_t)WV_THREADS * (CL_TCAP + CL_WCAP) * sizeof(uint32_t);
 
 struct ClShared {
     SerialShared ser;
     uint32_t     words[WV_SMEM_WORDS];
-    uint32_t     mask[8 * WV_THREADS];          // as in WvShared
-    uint32_t     ck[8 * WV_THREADS];
+    uint32_t     mask[8 * WV_THREADS];          // [k][t]: token starts in bits 32k .. 32k+31 of subsequence t
+    uint32_t     pf_tail[16];                   // (the bulk prefetch of the next wave's words lands in mask ++ pf_tail)
     uint32_t     exit_[WV_THREADS];
     uint32_t     wpos_[WV_THREADS];
     uint32_t     wn_[WV_THREADS];
     uint64_t     cross_[WV_THREADS];
     uint16_t     wc_[WV_THREADS];
+    uint16_t     wk_[WV_THREADS];               // tokens the walk has decoded (staged in walk[u][..] up to CL_WCAP)
     uint16_t     next_[WV_THREADS];
     uint8_t      kind_[WV_THREADS];
     uint8_t      wlist[2][WV_THREADS];
@@ -76,22 +90,107 @@ struct ClShared {
     WvHeader     hdr;
     uint16_t     cells[CL_SLOTS] __align__(32);
 };
-static_assert(sizeof(ClShared) <= (228 * 1024 - CL_CTAS_PER_SM * 1024) / CL_CTAS_PER_SM, "three CTAs per SM");
+static_assert(sizeof(ClShared) <= (228 * 1024 - CL_CTAS_PER_SM * 1024) / CL_CTAS_PER_SM, "CTAs per SM");
 static_assert(CL_SLOTS <= 16384 && CL_SLOTS % 16 == 0, "14-bit cell index");
 
-typedef volatile uint16_t* cellp_t;
+// Shared memory by explicit 32-bit shared-window addresses (st.shared / ld.shared / red.shared): with 80 registers
+// per thread the compiler otherwise rebuilds the window base from SR_CgaCtaId inside the hot loops (ncu r02: an S2R
+// at the top of every decode iteration), and cells must be accessed exactly as written (racing sweeps).
+#ifdef PNGB200_EMU
+inline void     sts16(saddr_t a, uint32_t v) { *(volatile uint16_t*)a = (uint16_t)v; }
+inline uint32_t lds16(saddr_t a) { return *(volatile uint16_t*)a; }
+inline void     sts32(saddr_t a, uint32_t v) { *(volatile uint32_t*)a = v; }
+inline void     reds_or(saddr_t a, uint32_t v) { *(volatile uint32_t*)a |= v; }
+inline saddr_t  opaque(saddr_t a) { return a; }
+#else
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void reds_or(uint32_t a, uint32_t v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t a)   // a value the compiler cannot rematerialise: it stays in a register
+{
+    asm volatile("" : "+r"(a));
+    return a;
+}
+#endif
+typedef saddr_t cellp_t;   // shared-window address of cells[0]
 
-// the pointer cells of one LZ77 copy: destination slots [j, j + run), first slot of the wave `jbeg`
+// Decode one token at the reader's position: the loop body of phases A, B and of the emit fallback.  One predicated
+// body for literals and copies (a warp always holds both), and ONE rarely taken branch per table for everything that is
+// not a plain root entry (subtable pointer, end of block, invalid code) -- wv_decode tests pointer and special
+// separately, ~8 instructions more per token.  Returns 0, PF_EOB (consumed) or PF_BAD.  `tok` = run << 16 | distance
+// for a copy (distance 1 .. 32768), byte << 16 for a literal; `nbytes`: bytes the token produces; `cp`: 1 for a copy.
+__device__ __forceinline__ uint32_t cl_decode(FastBits& b, saddr_t lit, saddr_t dst, uint32_t& tok, uint32_t& nbytes, uint32_t& cp)
+{
+    const uint32_t bits = b.peek();
+    uint32_t e = lds32(lit + ((bits & ((1u << LIT_ROOT) - 1u)) << 2));
+    if (e & E_SPECIAL) {
+        if ((e & (E_PTR | E_INVALID)) == E_PTR) e = lds32(lit + (((e >> 16) + bfe32(bits, LIT_ROOT, e_skip(e) - LIT_ROOT)) << 2));
+        if (e & E_SPECIAL) {
+            if (e & E_INVALID) return PF_BAD;
+            b.skip(e_len(e));
+            return PF_EOB;
+        }
+    }
+    const uint32_t len = e & 15u, skipn = (e >> 4) & 31u;
+    const uint32_t run = (e >> 16) + bfe32(bits, len, skipn - len);   // literals: width 0, value = the byte
+    b.skip(skipn);
+    cp = (e >> 9) & 1u;
+    const uint32_t dbits = b.peek();
+    uint32_t d = lds32(dst + ((dbits & ((1u << DIST_ROOT) - 1u)) << 2));   // ignored for literals
+    if (d & E_SPECIAL) {
+        if ((d & (E_PTR | E_INVALID)) == E_PTR) d = lds32(dst + (((d >> 16) + bfe32(dbits, DIST_ROOT, e_skip(d) - DIST_ROOT)) << 2));
+        if (cp && (d & E_SPECIAL)) return PF_BAD;
+    }
+    const uint32_t dlen = d & 15u, dskip = (d >> 4) & 31u;
+    const uint32_t dist = (d >> 16) + bfe32(dbits, dlen, dskip - dlen);
+    b.skip(cp ? dskip : 0u);
+    tok = run << 16 | (cp ? dist : 0u);
+    nbytes = cp ? run : 1u;
+    return 0;
+}
+__device__ __forceinline__ uint32_t tok_bytes(uint32_t v) { return (v & 0xffffu) ? v >> 16 : 1u; }
+
+// the pointer cells of one LZ77 copy: destination slots [j, j + run), first slot of the wave `jbeg`.  Most copies in
+// PNG data are 3 or 4 bytes long and lie entirely on one side of the wave's first byte: their cells are four
+// predicated stores, no loop (a loop per copy ran at 6 of 32 lanes: copies of different lengths side by side).
 __device__ __forceinline__ void cells_copy(cellp_t ch, uint32_t j, uint32_t run, uint32_t dist, uint32_t jbeg)
 {
-    const int32_t  src  = (int32_t)j - (int32_t)dist;                 // slot of the first source byte (may lie in front of the wave)
-    const uint32_t nwin = src >= (int32_t)jbeg ? 0u : min(run, (uint32_t)((int32_t)jbeg - src));
-    // window part: position relative to the wave's first byte = src + k - jbeg, in [-32768, -1]
+    const int32_t src = (int32_t)j - (int32_t)dist;                  // slot of the first source byte (may lie in front of the wave)
+    const saddr_t to = ch + 2 * j;
+    if (src >= (int32_t)jbeg || src + (int32_t)run <= (int32_t)jbeg) {
+        // all in-wave (cell = 0xc000 + source slot) or all window (cell = 0x8100 + position relative to the wave's
+        // first byte, in [-32768, -1])
+        const uint32_t code = src >= (int32_t)jbeg ? CL_INWAVE + (uint32_t)src
+                                                   : (uint32_t)((int32_t)CL_WINDOW_BIAS + src - (int32_t)jbeg);
+        sts16(to, code);
+        sts16(to + 2, code + 1);
+        sts16(to + 4, code + 2);
+        if (run > 3) sts16(to + 6, code + 3);
+        for (uint32_t k = 4; k < run; ++k) sts16(to + 2 * k, code + k);
+        return;
+    }
+    // the source starts in front of the wave and runs into it
+    const uint32_t nwin = (uint32_t)((int32_t)jbeg - src);
     uint32_t code = (uint32_t)((int32_t)CL_WINDOW_BIAS + src - (int32_t)jbeg);
     uint32_t k = 0;
-    for (; k < nwin; ++k) ch[j + k] = (uint16_t)(code + k);
-    code = CL_INWAVE + (uint32_t)src;                                 // src + k >= jbeg >= 0 from here on
-    for (; k < run; ++k) ch[j + k] = (uint16_t)(code + k);
+    for (; k < nwin; ++k) sts16(to + 2 * k, code + k);
+    code = CL_INWAVE + (uint32_t)src;
+    for (; k < run; ++k) sts16(to + 2 * k, code + k);
 }
 
 __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kernel(WvParams P)
@@ -101,13 +200,21 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
     const uint32_t t    = threadIdx.x;
     const unsigned lane = lane_id(), warp = t >> 5;
     if (t == 0) mbar_init(&sh.pf_bar, 1);
-    static_assert(offsetof(ClShared, ck) == offsetof(ClShared, mask) + sizeof(uint32_t) * 8 * WV_THREADS, "prefetch area = mask ++ ck");
+    static_assert(offsetof(ClShared, pf_tail) == offsetof(ClShared, mask) + sizeof(uint32_t) * 8 * WV_THREADS &&
+                  sizeof(uint32_t) * WV_PF_WORDS <= sizeof(uint32_t) * (8 * WV_THREADS + 16), "prefetch area = mask ++ pf_tail");
     static_assert(offsetof(ClShared, mask) % 16 == 0 && offsetof(ClShared, cells) % 32 == 0, "alignment");
     uint32_t pf_parity = 0;
-    const saddr_t words_addr = smem_addr(sh.words);
-    const saddr_t lit = smem_addr(sh.ser.lit), dstt = smem_addr(sh.ser.dist);
+    const saddr_t sbase = opaque(smem_addr(cl_smem));
+    const saddr_t words_addr = sbase + offsetof(ClShared, words);
+    const saddr_t lit = sbase + offsetof(ClShared, ser) + offsetof(SerialShared, lit);
+    const saddr_t dstt = sbase + offsetof(ClShared, ser) + offsetof(SerialShared, dist);
+    const saddr_t mk_t = sbase + offsetof(ClShared, mask) + 4 * t;     // my column of the token-start maps: word k at + 1024 k
+    const saddr_t mk_0 = sbase + offsetof(ClShared, mask);
     uint32_t* const mk = sh.mask;
-    cellp_t const ch = sh.cells;
+    cellp_t const ch = sbase + offsetof(ClShared, cells);
+    uint32_t* const tok_own  = reinterpret_cast<uint32_t*>(P.scratch + blockIdx.x * P.scratch_stride);
+    uint32_t* const tok_walk = tok_own + WV_THREADS * CL_TCAP;
+    uint32_t* const tok_mine = tok_own + t * CL_TCAP;
 
     for (;;) {
         __syncthreads();
@@ -259,32 +366,24 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
 
                     // ---- A. speculative decode of my subsequence: token-start map, checkpoints, totals ----
                     uint32_t nout = 0, ncopy = 0, flags = 0, exit_bit = base;
+                    uint32_t n = 0;                 // tokens of my own decode (staged in tok_own[t][..] up to CL_TCAP)
                     {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) mk[k * WV_THREADS + t] = 0;
-                        sh.ck[t] = 0;
-                        uint32_t n = 0;
+                        for (int k = 0; k < 8; ++k) sts32(mk_t + 1024 * k, 0);
                         if (t < nsub) {
                             FastBits b;
                             b.init(words_addr, t == 0 ? rel0 : base);
-                            uint32_t mi = 0, mw = 0;
                             while (b.pos < limit) {
-                                const uint32_t rr = b.pos - base, wi = rr >> 5;
-                                if (wi != mi) {
-                                    mk[mi * WV_THREADS + t] = mw;
-                                    mw = 0;
-                                    mi = wi;
-                                    sh.ck[wi * WV_THREADS + t] = nout | ncopy << 16;
-                                }
-                                mw |= 1u << (rr & 31);
-                                uint32_t run = 0, dist = 0, cp = 0;
-                                const uint32_t s = wv_decode<false>(b, lit, dstt, run, dist, cp);
+                                const uint32_t rr = b.pos - base;
+                                reds_or(mk_t + ((rr >> 5) << 10), 1u << (rr & 31));     // this position starts a token
+                                uint32_t tok = 0, nb = 0, cp = 0;
+                                const uint32_t s = cl_decode(b, lit, dstt, tok, nb, cp);
                                 if (s) { flags = s; break; }
-                                nout += cp ? run : 1u;
+                                if (n < CL_TCAP) tok_mine[n] = tok;
+                                nout += nb;
                                 ncopy += cp;
                                 ++n;
                             }
-                            mk[mi * WV_THREADS + t] = mw;
                             exit_bit = b.pos;
                         } else {
                             flags = PF_BAD;       // not part of this wave: never reached by the chain
@@ -298,8 +397,9 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
 
                     // ---- B. walks (as in inflate_wave_kernel) ----
                     {
-                        uint32_t u = t, pos = exit_bit, wn = 0, wc = 0;
+                        uint32_t u = t, pos = exit_bit, wn = 0, wc = 0, wk = 0;
                         bool     active = flags == 0;
+                        sh.wk_[t] = 0;
                         if (!active) {
                             sh.kind_[t] = (uint8_t)(flags == PF_EOB ? WK_OWN_EOB : WK_OWN_BAD);
                             sh.wpos_[t] = exit_bit;
@@ -321,19 +421,24 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                                     if (p >= wave_bits) { kind = WK_END; break; }
                                     const uint32_t s = p >> 8, rr = p & 255u;
                                     if (!crossed && s > first_sub) {
-                                        sh.cross_[u] = 1ull << 63 | (uint64_t)p << 40 | (uint64_t)(wc & 0xffu) << 24 | (wn & 0xffffffu);
+                                        // (bits 32..39: walk tokens in front of the crossing, 255 = more than the staging keeps)
+                                        sh.cross_[u] = 1ull << 63 | (uint64_t)p << 40 | (uint64_t)min(wk, 255u) << 32 |
+                                                       (uint64_t)(wc & 0xffu) << 24 | (wn & 0xffffffu);
                                         crossed = true;
                                     }
-                                    if ((mk[(rr >> 5) * WV_THREADS + s] >> (rr & 31)) & 1u) { kind = WK_SYNC; break; }
-                                    uint32_t run = 0, dist = 0, cp = 0;
-                                    const uint32_t e = wv_decode<false>(b, lit, dstt, run, dist, cp);
+                                    if ((lds32(mk_0 + (((rr >> 5) << 10) + (s << 2))) >> (rr & 31)) & 1u) { kind = WK_SYNC; break; }
+                                    uint32_t tok = 0, nb = 0, cp = 0;
+                                    const uint32_t e = cl_decode(b, lit, dstt, tok, nb, cp);
                                     if (e) { kind = e == PF_EOB ? WK_EOB : WK_BAD; break; }
-                                    wn += cp ? run : 1u;
+                                    if (wk < CL_WCAP) tok_walk[u * CL_WCAP + wk] = tok;
+                                    ++wk;
+                                    wn += nb;
                                     wc += cp;
                                 }
                                 sh.wpos_[u] = b.pos;
                                 sh.wn_[u]   = wn;
                                 sh.wc_[u]   = (uint16_t)wc;
+                                sh.wk_[u]   = (uint16_t)min(wk, 0xffffu);
                                 sh.kind_[u] = (uint8_t)kind;
                                 still = kind == WK_RUNNING;
                                 walk_tokens += iters;
@@ -357,6 +462,7 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                                 pos = sh.wpos_[u];
                                 wn  = sh.wn_[u];
                                 wc  = sh.wc_[u];
+                                wk  = sh.wk_[u];
                             }
                         }
                     }
@@ -409,8 +515,14 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                     uint32_t from = rel0, to = exit_bit;
                     uint32_t my_nout = 0, my_ncopy = 0;
                     bool     adopted = false;
+                    // my share as staged tokens: walk tokens [a_lo, a_hi) of thread a_src, then my own tokens [b_lo, n),
+                    // then (last thread of the chain) my own walk's tokens; `kept`: all of them were kept by the staging
+                    uint32_t a_src = 0, a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0, c_hi = 0;
+                    bool     kept = true;
                     if (on_chain) {
                         uint32_t pn = 0, pc = 0, pre_n = 0, pre_c = 0;
+                        b_hi = n;
+                        kept = n <= CL_TCAP;
                         if (t > 0) {
                             uint32_t w = warp, m = sh.valid[w] & ((1u << lane) - 1u);
                             while (m == 0) m = sh.valid[--w];
@@ -419,26 +531,37 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                             from = sh.exit_[pred];
                             pn = sh.wn_[pred];
                             pc = sh.wc_[pred];
+                            a_src = pred;
+                            a_hi = sh.wk_[pred];
+                            kept = kept && a_hi <= CL_WCAP;
                             if (pred + 1 < t) {
                                 const uint64_t cr = sh.cross_[pred];
                                 if (cr) {
                                     from = (uint32_t)(cr >> 40) & 0x1ffffu;
                                     pn -= (uint32_t)cr & 0xffffffu;
                                     pc -= (uint32_t)(cr >> 24) & 0xffu;
+                                    a_lo = (uint32_t)(cr >> 32) & 0xffu;
+                                    kept = kept && a_lo != 255u;
                                 }
                             }
                             const uint32_t rr = p0 - base, q = rr >> 5;
-                            const uint32_t ck = sh.ck[q * WV_THREADS + t];
-                            pre_n = ck & 0xffffu;
-                            pre_c = ck >> 16;
-                            const uint32_t first = (uint32_t)__ffs((int)mk[q * WV_THREADS + t]) - 1;
-                            if (first != (rr & 31)) {
+                            // my tokens in front of p0 (the garbage prefix) = the token starts my map holds below p0;
+                            // their bytes and copies are summed from the staged tokens
+                            for (uint32_t k = 0; k < q; ++k) b_lo += (uint32_t)__popc(mk[k * WV_THREADS + t]);
+                            b_lo += (uint32_t)__popc(mk[q * WV_THREADS + t] & ((1u << (rr & 31)) - 1u));
+                            if (b_lo <= CL_TCAP) {
+                                for (uint32_t k = 0; k < b_lo; ++k) {
+                                    const uint32_t v = tok_mine[k];
+                                    pre_n += tok_bytes(v);
+                                    pre_c += (v & 0xffffu) != 0;
+                                }
+                            } else {
                                 FastBits b;
-                                b.init(words_addr, base + 32 * q + first);
+                                b.init(words_addr, base);
                                 while (b.pos != p0 && b.pos < limit) {
-                                    uint32_t run = 0, dist = 0, cp = 0;
-                                    if (wv_decode<false>(b, lit, dstt, run, dist, cp)) break;
-                                    pre_n += cp ? run : 1u;
+                                    uint32_t tok = 0, nb = 0, cp = 0;
+                                    if (cl_decode(b, lit, dstt, tok, nb, cp)) break;
+                                    pre_n += nb;
                                     pre_c += cp;
                                 }
                             }
@@ -449,6 +572,8 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                             to = wpos;
                             my_nout += sh.wn_[t];
                             my_ncopy += sh.wc_[t];
+                            c_hi = sh.wk_[t];
+                            kept = kept && c_hi <= CL_WCAP;
                             if (term == WK_BAD || term == WK_OWN_BAD || (wbase << 5) + wpos > br.total_bits)
                                 sh.anomaly = 1;
                         }
@@ -461,6 +586,9 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                             to       = (uint32_t)(cr >> 40) & 0x1ffffu;
                             my_nout  = (uint32_t)cr & 0xffffffu;
                             my_ncopy = (uint32_t)(cr >> 24) & 0xffu;
+                            a_src    = t - 1;
+                            a_hi     = (uint32_t)(cr >> 32) & 0xffu;
+                            kept   = a_hi != 255u && a_hi <= CL_WCAP;
                         }
                     }
                     const uint64_t mine = (uint64_t)my_ncopy << 40 | my_nout;
@@ -509,8 +637,45 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                     uint8_t* const wdst  = dst + out;                        // HBM address of wave offset 0
                     const uint32_t shift = (uint32_t)((uintptr_t)wdst & 15); // slot of wave offset 0 (dst's 16-byte phase)
                     const uint32_t reach = out >= WV_WINDOW ? 0x7fffffffu : (uint32_t)out;
-                    uint32_t emitted = 0, my_stop = 0xffffffffu, o = 0;
-                    if ((on_chain || adopted) && from != to) {
+                    uint32_t emitted = 0, my_stop = 0xffffffffu, o = 0, from_staging = 0;
+#ifdef CL_NO_STAGING
+                    kept = false;
+#endif
+                    if ((on_chain || adopted) && from != to && !cut && kept) {
+                        // my share was kept by the passes that decoded it: read it back (walk piece, own piece, own walk)
+                        o = (uint32_t)o64;
+                        bool bad_ref = false;
+                        auto piece = [&](const uint32_t* p, uint32_t lo, uint32_t hi) {
+                            for (uint32_t i = lo; i < hi && !bad_ref; i += 4) {
+                                uint32_t tk[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) tk[q] = i + q < hi ? p[i + q] : 0u;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (i + q >= hi || bad_ref) break;
+                                    const uint32_t v = tk[q];
+                                    const uint32_t dist = v & 0xffffu, run = v >> 16;
+                                    if (dist == 0) {
+                                        sts16(ch + 2 * (shift + o), run);
+                                        o += 1;
+                                    } else {
+                                        if (dist > reach + o) { bad_ref = true; break; }
+                                        cells_copy(ch, shift + o, run, dist, shift);
+                                        o += run;
+                                    }
+                                    ++emitted;
+                                }
+                            }
+                        };
+                        piece(tok_walk + a_src * CL_WCAP, a_lo, a_hi);
+                        piece(tok_mine, b_lo, b_hi);
+                        piece(tok_walk + t * CL_WCAP, 0, c_hi);
+                        if (bad_ref) sh.anomaly = 1;
+                        from_staging = emitted;
+#ifdef PNGB200_EMU
+                        if (!bad_ref && o != (uint32_t)o64 + my_nout) { fprintf(stderr, "cells: kept share of thread %u is %u bytes, expected %u\n", t, o - (uint32_t)o64, my_nout); abort(); }
+#endif
+                    } else if ((on_chain || adopted) && from != to) {
                         if (o64 >= CL_CAP) {
                             my_stop = from;                  // nothing of my share fits
                             o = CL_CAP;                      // (if I am the first such thread, the shares in front end exactly here)
@@ -520,21 +685,22 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                             FastBits b;
                             b.init(words_addr, from);
                             while (b.pos != to && b.pos < wave_bits + 64) {
-                                const uint32_t tok = b.pos;
-                                uint32_t run = 0, dist = 0, cp = 0;
-                                if (wv_decode<true>(b, lit, dstt, run, dist, cp)) break;
-                                const uint32_t n = cp ? run : 1u;
-                                if (o + n > CL_CAP) { my_stop = tok; break; }
-                                if (!cp) ch[shift + o] = (uint16_t)run;
+                                const uint32_t at = b.pos;
+                                uint32_t tok = 0, nb = 0, cp = 0;
+                                if (cl_decode(b, lit, dstt, tok, nb, cp)) break;
+                                if (o + nb > CL_CAP) { my_stop = at; break; }
+                                const uint32_t dist = tok & 0xffffu, run = tok >> 16;
+                                if (!cp) sts16(ch + 2 * (shift + o), run);
                                 else if (dist > reach + o) { bad_ref = true; break; }   // invalidStringReference: the serial decoder reports it
                                 else cells_copy(ch, shift + o, run, dist, shift);
-                                o += n;
+                                o += nb;
                                 ++emitted;
                             }
                             if (bad_ref) sh.anomaly = 1;
                         }
                     }
                     WV_COUNT(2, emitted);
+                    WV_COUNT(3, from_staging);
                     if (cut && my_stop != 0xffffffffu) atomicMin(&sh.cut_pos, my_stop);
                     __syncthreads();                                      // (7) cells written
                     tick(6);
@@ -555,26 +721,36 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                         const uint32_t wlo = jbeg >> 1, whi = (jend + 1) >> 1;
                         const uint32_t per = ((whi - wlo + WV_THREADS - 1) / WV_THREADS) | 1u;   // odd word stride: no bank conflicts
                         const uint32_t a = min(wlo + t * per, whi), e = min(a + per, whi);
-                        volatile uint32_t* const cw = reinterpret_cast<volatile uint32_t*>(sh.cells);
                         uint32_t rounds = 0;
+                        bool     mine = true;               // my chunk may still hold in-wave pointers
                         for (;;) {
                             bool more = false;
-                            for (uint32_t i = a; i < e; ++i) {
-                                const uint32_t w = cw[i];
-                                uint32_t c0 = w & 0xffffu, c1 = w >> 16;
-                                const bool p0 = c0 >= CL_INWAVE && 2 * i >= jbeg;
-                                const bool p1 = c1 >= CL_INWAVE && 2 * i + 1 < jend;
-                                if (p0) {
-                                    c0 = ch[c0 & 0x3fffu];
-                                    ch[2 * i] = (uint16_t)c0;
-                                    more |= c0 >= CL_INWAVE;
+                            if (mine) {
+                                for (uint32_t i = a; i < e; ++i) {
+                                    const uint32_t w = lds32(ch + 4 * i);
+                                    if ((w & (w << 1) & 0x80008000u) == 0) continue;      // no in-wave pointer in this word
+                                    uint32_t c0 = w & 0xffffu, c1 = w >> 16;
+                                    const bool p0 = c0 >= CL_INWAVE && 2 * i >= jbeg;
+                                    const bool p1 = c1 >= CL_INWAVE && 2 * i + 1 < jend;
+                                    if (p0) {
+                                        // follow the chain a few hops at once: inside my chunk the first hop already lands
+                                        // on a swept cell; across chunks the owner may not have got there yet
+                                        c0 = lds16(ch + 2 * (c0 & 0x3fffu));
+#pragma unroll 1
+                                        for (int hop = 0; hop < 3 && c0 >= CL_INWAVE; ++hop) c0 = lds16(ch + 2 * (c0 & 0x3fffu));
+                                        sts16(ch + 4 * i, c0);
+                                        more |= c0 >= CL_INWAVE;
+                                    }
+                                    if (p1) {
+                                        const uint32_t j1 = c1 & 0x3fffu;
+                                        c1 = j1 == 2 * i ? c0 : lds16(ch + 2 * j1);
+#pragma unroll 1
+                                        for (int hop = 0; hop < 3 && c1 >= CL_INWAVE; ++hop) c1 = lds16(ch + 2 * (c1 & 0x3fffu));
+                                        sts16(ch + 4 * i + 2, c1);
+                                        more |= c1 >= CL_INWAVE;
+                                    }
                                 }
-                                if (p1) {
-                                    const uint32_t j1 = c1 & 0x3fffu;
-                                    c1 = j1 == 2 * i ? c0 : ch[j1];
-                                    ch[2 * i + 1] = (uint16_t)c1;
-                                    more |= c1 >= CL_INWAVE;
-                                }
+                                mine = more;
                             }
                             ++rounds;
                             if (!__syncthreads_or(more)) break;

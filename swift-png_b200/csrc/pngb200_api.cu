@@ -448,7 +448,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             if (ctx->inflate_mode == 6) engine = ENG_CELLS;
             const bool use_wave = engine == ENG_WAVE;
             const uint64_t bitmap_words = engine == ENG_CELLS ? 8 : use_wave ? wv_bitmap_words(max_cap) : par_bitmap_words(max_cap);
-            const uint64_t stride = engine == ENG_CELLS ? 256 : use_wave ? wv_scratch_stride(bitmap_words) : par_scratch_stride(bitmap_words);
+            const uint64_t stride = engine == ENG_CELLS ? CL_SCRATCH : use_wave ? wv_scratch_stride(bitmap_words) : par_scratch_stride(bitmap_words);
             unsigned grid = (unsigned)std::min<size_t>(par.size(), engine == ENG_CELLS ? (size_t)ctx->sm_count * CL_CTAS_PER_SM
                                                                    : use_wave         ? wave_slots
                                                                                       : (size_t)ctx->sm_count * PAR_CTAS_PER_SM);
@@ -468,6 +468,8 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             hooked = true;
             if (engine == ENG_CELLS) {
                 WvParams pp{};
+                pp.scratch = ctx->d_scratch.as<uint8_t>();
+                pp.scratch_stride = stride;
                 pp.ticket = ticket;
                 pp.jobs = d_jobs;
                 pp.results = d_results;

@@ -14,6 +14,9 @@ extern "C" int emu_inflate_cells(const uint8_t* src, uint64_t len, uint8_t* dst,
     uint32_t ticket = 0;
     WvParams P{};
     P.jobs = &job; P.results = res; P.order = nullptr; P.ticket = &ticket; P.count = 1;
+    std::vector<uint8_t> scratch(CL_SCRATCH + 256, 0);
+    P.scratch = scratch.data();
+    P.scratch_stride = CL_SCRATCH;
     simt::launch(1, WV_THREADS, sizeof(ClShared), [&]() { inflate_cells_kernel(P); }, order);
     return res->status;
 }
