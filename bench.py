@@ -334,6 +334,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = ctx.launches - launches0
     stats = ctx.inflate_counters(B)
+    engine_used = ctx.last_inflate_engine()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -474,7 +475,7 @@ def main():
     comp_step = sum(len(items[i % len(items)]["idat"]) for i in range(B))
     alg_bytes = comp_step + B * storage_bytes  # C + P per image x images per launch
     dominant = int(np.argmax(stage))
-    inflate_kernel = "inflate_wave_kernel" if B <= 296 else "inflate_parallel_kernel"  # pngb200_api.cu run_inflate
+    inflate_kernel = engine_used or ("inflate_wave_kernel" if B <= 296 else "inflate_parallel_kernel")  # as reported by run_inflate
     names = [inflate_kernel, "checksum kernels", "unfilter_wave_kernel"]
     achieved = alg_bytes / (stage[0] / 1e3) / 1e9
     traffic, issue = None, None

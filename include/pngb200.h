@@ -139,6 +139,9 @@ int          pngb200_ctx_inflate_counters(pngb200_ctx* ctx, size_t count, uint64
  * decode batch on this context: out[0] streams that were cut, out[1] segments they were cut into, out[2] streams
  * whose segments did not line up and that were decoded whole after all (results are identical either way). */
 int          pngb200_ctx_segment_stats(pngb200_ctx* ctx, uint64_t out[3]);
+/* which whole-stream engine the last inflate / decode batch on this context launched: 0 inflate_parallel_kernel
+ * (round 1), 1 inflate_wave_kernel (ring window), 2 inflate_cells_kernel, -1 none (tiny streams, segments only) */
+int          pngb200_ctx_last_inflate_engine(pngb200_ctx* ctx);
 /* scanlines per filter type of the last decode / unfilter batch that went through the wavefront kernel
  * (non-interlaced, >= 8 bits per sample): out[0..4] = None, Sub, Up, Average, Paeth, out[5] = rows with an
  * invalid filter byte (left unchanged, as the reference does).  The device-side form of the reference's

@@ -236,6 +236,9 @@ def lib():
     L.pngb200_ctx_filter_histogram.restype = C.c_int
     L.pngb200_ctx_segment_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_segment_stats.restype = C.c_int
+    if os.environ.get("PNGB200_LIB") is None or hasattr(L, "pngb200_ctx_last_inflate_engine"):   # (older tuning builds lack it)
+        L.pngb200_ctx_last_inflate_engine.argtypes = [C.c_void_p]
+        L.pngb200_ctx_last_inflate_engine.restype = C.c_int
     L.pngb200_ctx_inflate_counters.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
     L.pngb200_ctx_inflate_counters.restype = C.c_int
     L.pngb200_inflate_batch.argtypes = [C.c_void_p, C.POINTER(StreamDesc), C.c_size_t, C.c_int]
@@ -355,6 +358,13 @@ class Context:
         out = (C.c_uint64 * 3)()
         self.check(self._lib.pngb200_ctx_segment_stats(self.handle, out))
         return dict(streams=out[0], segments=out[1], fallbacks=out[2])
+
+    def last_inflate_engine(self) -> str:
+        """kernel name of the whole-stream inflate engine the last batch used ('' when none ran)"""
+        if not hasattr(self._lib, "pngb200_ctx_last_inflate_engine"):
+            return ""
+        return {0: "inflate_parallel_kernel", 1: "inflate_wave_kernel", 2: "inflate_cells_kernel"}.get(
+            self._lib.pngb200_ctx_last_inflate_engine(self.handle), "")
 
     def set_inflate_mode(self, mode: int):
         self._lib.pngb200_ctx_set_inflate_mode(self.handle, mode)

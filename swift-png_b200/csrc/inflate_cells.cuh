@@ -769,29 +769,52 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                             // a window cell: relative position c - 0x8100 in [-32768, -1]
                             return c < 256u ? c : (uint32_t)wdst[(int32_t)c - (int32_t)CL_WINDOW_BIAS];
                         };
-                        for (uint32_t c = t; c < nq; c += WV_THREADS) {
-                            const uint32_t lo = c << 4, hi = lo + 16;
-                            if (lo >= shift && hi <= end) {
-                                const uint4 h0 = *reinterpret_cast<const uint4*>(sh.cells + lo);
-                                const uint4 h1 = *reinterpret_cast<const uint4*>(sh.cells + lo + 8);
-                                const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                                uint32_t by[4];
+                        // 16 cells -> 16 bytes; the window gathers of TWO chunks are in flight before either is packed (the
+                        // phase is bound by the L2 round trip of those byte loads)
+                        auto fetch = [&](uint32_t lo, uint32_t (&v)[16]) {
+                            const uint4 h0 = *reinterpret_cast<const uint4*>(sh.cells + lo);
+                            const uint4 h1 = *reinterpret_cast<const uint4*>(sh.cells + lo + 8);
+                            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint32_t b0 = cell_byte(hw[2 * q] & 0xffffu), b1 = cell_byte(hw[2 * q] >> 16);
-                                    const uint32_t b2 = cell_byte(hw[2 * q + 1] & 0xffffu), b3 = cell_byte(hw[2 * q + 1] >> 16);
-                                    by[q] = b0 | b1 << 8 | b2 << 16 | b3 << 24;
-                                }
-                                const uint4 x = make_uint4(by[0], by[1], by[2], by[3]);
-                                reinterpret_cast<uint4*>(gbase)[c] = x;
-                                adler_chunk16_u32(x, end - lo, a, bw);
-                            } else {
-                                for (uint32_t k = max(lo, shift); k < min(hi, end); ++k) {
-                                    const uint32_t v = cell_byte(sh.cells[k]);
-                                    gbase[k] = (uint8_t)v;
-                                    a += v;
-                                    bw += (end - k) * v;
-                                }
+                            for (int q = 0; q < 8; ++q) {
+                                v[2 * q]     = cell_byte(hw[q] & 0xffffu);
+                                v[2 * q + 1] = cell_byte(hw[q] >> 16);
+                            }
+                        };
+                        auto pack = [&](const uint32_t (&v)[16]) -> uint4 {
+                            uint32_t by[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) by[q] = v[4 * q] | v[4 * q + 1] << 8 | v[4 * q + 2] << 16 | v[4 * q + 3] << 24;
+                            return make_uint4(by[0], by[1], by[2], by[3]);
+                        };
+                        const uint32_t qlo = (shift + 15) >> 4, qhi = end >> 4;       // chunks [qlo, qhi) are whole
+                        uint32_t c = qlo + t;
+                        for (; c + WV_THREADS < qhi; c += 2 * WV_THREADS) {
+                            uint32_t v0[16], v1[16];
+                            fetch(c << 4, v0);
+                            fetch((c + WV_THREADS) << 4, v1);
+                            const uint4 x0 = pack(v0), x1 = pack(v1);
+                            reinterpret_cast<uint4*>(gbase)[c] = x0;
+                            reinterpret_cast<uint4*>(gbase)[c + WV_THREADS] = x1;
+                            adler_chunk16_u32(x0, end - (c << 4), a, bw);
+                            adler_chunk16_u32(x1, end - ((c + WV_THREADS) << 4), a, bw);
+                        }
+                        if (c < qhi) {
+                            uint32_t v0[16];
+                            fetch(c << 4, v0);
+                            const uint4 x0 = pack(v0);
+                            reinterpret_cast<uint4*>(gbase)[c] = x0;
+                            adler_chunk16_u32(x0, end - (c << 4), a, bw);
+                        }
+                        // the ragged head and tail (at most 15 bytes each): threads 0 and 1
+                        if (t < 2) {
+                            const uint32_t k0 = t == 0 ? shift : max(qhi << 4, shift), k1 = t == 0 ? min(qlo << 4, end) : end;
+                            const bool     skip = t == 1 && qhi < qlo;      // (everything lies inside one chunk: thread 0 took it)
+                            for (uint32_t k = k0; k < k1 && !skip; ++k) {
+                                const uint32_t v = cell_byte(sh.cells[k]);
+                                gbase[k] = (uint8_t)v;
+                                a += v;
+                                bw += (end - k) * v;
                             }
                         }
                         if (adler_on) {

@@ -96,6 +96,7 @@ struct pngb200_ctx {
     cudaStream_t stream = nullptr;
     uint64_t     launches = 0;
     int          inflate_mode = 0;
+    int          last_engine = -1;       // whole-stream engine of the last batch: 0 round-1, 1 ring, 2 cells, -1 none
     bool         cells_auto = false;     // automatic mode may pick inflate_cells_kernel (set once measured faster)
     int          sm_count = 148;
     std::string  error;
@@ -372,6 +373,7 @@ int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t
 // h_jobs: host copy (for dst_cap based chunk layout); d_jobs/d_results device arrays of `count`.
 int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
 {
+    ctx->last_engine = -1;
     StreamJob*    d_jobs    = ctx->d_jobs.as<StreamJob>();
     StreamResult* d_results = ctx->d_results.as<StreamResult>();
     ctx->seg_streams = ctx->seg_segments = ctx->seg_fallbacks = 0;
@@ -447,6 +449,7 @@ int run_inflate(pngb200_ctx* ctx, const StreamJob* h_jobs, size_t count)
             if (ctx->inflate_mode == 4) engine = ENG_PARALLEL;
             if (ctx->inflate_mode == 6) engine = ENG_CELLS;
             const bool use_wave = engine == ENG_WAVE;
+            ctx->last_engine = engine;
             const uint64_t bitmap_words = engine == ENG_CELLS ? 8 : use_wave ? wv_bitmap_words(max_cap) : par_bitmap_words(max_cap);
             const uint64_t stride = engine == ENG_CELLS ? CL_SCRATCH : use_wave ? wv_scratch_stride(bitmap_words) : par_scratch_stride(bitmap_words);
             unsigned grid = (unsigned)std::min<size_t>(par.size(), engine == ENG_CELLS ? (size_t)ctx->sm_count * CL_CTAS_PER_SM
@@ -659,7 +662,7 @@ int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
         p.total_bands = (uint32_t)bands;
         unsigned grid = (unsigned)std::min<uint64_t>((bands + WAVE_WARPS - 1) / WAVE_WARPS,
                                                      (uint64_t)ctx->sm_count * 8);
-        unfilter_wave_kernel<<<grid, WAVE_WARPS * 32, 0, ctx->stream>>>(p);
+        unfilter_wave_kernel<<<grid, WAVE_WARPS * 32, WAVE_SMEM, ctx->stream>>>(p);
         ctx->launches++;
         CU(cudaGetLastError());
     }
@@ -809,6 +812,11 @@ pngb200_ctx* pngb200_ctx_create(int device)
         delete ctx;
         return nullptr;
     }
+    if (cudaFuncSetAttribute(unfilter_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WAVE_SMEM) != cudaSuccess) {
+        set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", (size_t)WAVE_SMEM);
+        delete ctx;
+        return nullptr;
+    }
     if (configure_inflate_cells() != 0) {
         set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(ClShared));
         delete ctx;
@@ -917,6 +925,8 @@ int pngb200_ctx_filter_histogram(pngb200_ctx* ctx, uint64_t out[6])
     }
     return PNGB200_OK;
 }
+
+int pngb200_ctx_last_inflate_engine(pngb200_ctx* ctx) { return ctx ? ctx->last_engine : -1; }
 
 int pngb200_ctx_segment_stats(pngb200_ctx* ctx, uint64_t out[3])
 {

@@ -119,17 +119,31 @@ struct WaveParams {
                                 // -DDUMP_FILTERED_SCANLINES view of a decode, PNG.Decoder.swift:96-98,128); may be null
 };
 
-constexpr int WAVE_WARPS   = 8;
+#ifndef PNGB200_WAVE_WARPS
+#define PNGB200_WAVE_WARPS 8
+#endif
+constexpr int WAVE_WARPS   = PNGB200_WAVE_WARPS;
 #ifndef PNGB200_WAVE_PUBLISH
 #define PNGB200_WAVE_PUBLISH 8
 #endif
 constexpr int WAVE_PUBLISH = PNGB200_WAVE_PUBLISH;  // publish progress every this many chunks
 
 // Asynchronous staging of a lane's own row (cp.async = LDGSTS: global -> shared memory without a register in
-// between).  Every lane keeps WAVE_DEPTH aligned 16-byte chunks of its row in flight in a private ring in shared
-// memory, so the HBM / L2 round trip of chunk j + WAVE_DEPTH overlaps the arithmetic of chunks j .. j + WAVE_DEPTH - 1
-// (r01: two chunks ahead in registers, 11.7 long-scoreboard stall cycles per issue).
-constexpr int WAVE_DEPTH = 8;
+// between).  Every lane keeps a private ring of WAVE_DEPTH aligned 16-byte chunks of its row in shared memory and
+// refills it in BURSTS of WAVE_BURST chunks (= one 128-byte line of its row at a time, two bursts ahead of the
+// arithmetic).  A warp touches 32 rows that lie pitch + 1 bytes apart; fetched 16 bytes per row and step (round 2,
+// first half: WAVE_BURST 1) every DRAM access was a lone 32-byte sector in its own DRAM page -- ~1.7 TB/s whatever the
+// prefetch depth.  A burst asks for the four sectors of a line back to back, so the memory controller serves them
+// from one row activation.  The reconstructed chunks leave the same way: WAVE_BURST chunks per lane collect in a
+// second small ring and are stored as one run of consecutive 16-byte stores (a full line per row for L2 to merge).
+#ifndef PNGB200_WAVE_BURST
+#define PNGB200_WAVE_BURST 1
+#endif
+constexpr int WAVE_BURST = PNGB200_WAVE_BURST;                 // chunks per refill (1: one chunk per step, as in round 2a)
+constexpr int WAVE_DEPTH = WAVE_BURST == 1 ? 8 : 3 * WAVE_BURST;   // ring slots per lane
+constexpr int WAVE_OUT   = WAVE_BURST == 1 ? 0 : WAVE_BURST;   // output chunks collected per lane before they are stored
+constexpr int WAVE_OUTM  = WAVE_OUT ? WAVE_OUT : 1;           // (modulus that is never zero)
+constexpr size_t WAVE_SMEM = sizeof(uint4) * 32 * (size_t)WAVE_WARPS * (WAVE_DEPTH + (WAVE_OUT ? WAVE_OUT : 0));
 __device__ __forceinline__ void cp_async16(uint4* smem, const uint4* gmem)
 {
 #ifdef PNGB200_EMU
@@ -154,7 +168,7 @@ __device__ __forceinline__ void cp_async_wait()   // at most N of this thread's 
 
 template <int BPP>
 __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_prev, uint32_t* prog_mine, uint4 (*ring)[32],
-                          unsigned long long* hist)
+                          uint4 (*oring)[32], unsigned long long* hist)
 {
     const unsigned lane   = lane_id();
     const uint32_t y      = band * 32 + lane;
@@ -198,10 +212,20 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
     // input chunk k of my row is cp.async group k of this thread: WAVE_DEPTH groups are opened here, one more per
     // step, so when chunk j is consumed the groups up to j + 1 must have landed = at most WAVE_DEPTH - 2 in flight
     if (active) {
+        if (WAVE_BURST == 1) {
 #pragma unroll
-        for (int k = 0; k < WAVE_DEPTH; ++k) {
-            if (k < nq) cp_async16(&ring[k][lane], inq + k);
-            cp_async_commit();
+            for (int k = 0; k < WAVE_DEPTH; ++k) {
+                if (k < nq) cp_async16(&ring[k][lane], inq + k);
+                cp_async_commit();
+            }
+        } else {
+            // two bursts (chunks 0 .. 2 WAVE_BURST - 1) are on their way before the first chunk is used; burst b is
+            // cp.async group b of this thread
+#pragma unroll
+            for (int k = 0; k < 2 * WAVE_BURST; ++k) {
+                if (k < nq) cp_async16(&ring[k][lane], inq + k);
+                if ((k + 1) % WAVE_BURST == 0) cp_async_commit();
+            }
         }
     }
 
@@ -237,13 +261,26 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
             }
         }
         if (active && j >= 0 && j < nchunk) {
-            cp_async_wait<WAVE_DEPTH - 2>();
+            if (WAVE_BURST == 1) cp_async_wait<WAVE_DEPTH - 2>();
+            else if (j % WAVE_BURST == 0) {
+                // burst j / WAVE_BURST + 2 (chunks j + 2 WAVE_BURST ...) goes into the slots the burst before this one
+                // has left; then everything but that newest group must have landed: chunks up to j + 2 WAVE_BURST - 1
+#pragma unroll
+                for (int k = 0; k < WAVE_BURST; ++k) {
+                    const int c = j + 2 * WAVE_BURST + k;
+                    if (c < nq) cp_async16(&ring[c % WAVE_DEPTH][lane], inq + c);
+                }
+                cp_async_commit();
+                cp_async_wait<1>();
+            }
             qcur = ring[j % WAVE_DEPTH][lane];
             const uint4 qnext = ring[(j + 1) % WAVE_DEPTH][lane];
             uint4 x = m == 0 ? qcur : shift_bytes(qcur, qnext, m);
-            // chunk j + WAVE_DEPTH takes the slot chunk j just left (x depends on the loads above: they are done)
-            if (j + WAVE_DEPTH < nq) cp_async16(&ring[j % WAVE_DEPTH][lane], inq + j + WAVE_DEPTH);
-            cp_async_commit();
+            if (WAVE_BURST == 1) {
+                // chunk j + WAVE_DEPTH takes the slot chunk j just left (x depends on the loads above: they are done)
+                if (j + WAVE_DEPTH < nq) cp_async16(&ring[j % WAVE_DEPTH][lane], inq + j + WAVE_DEPTH);
+                cp_async_commit();
+            }
             uint4 o;
             if (BPP == 4) {
                 o.x = __vadd4(x.x, predict4(type, a1, up.x, c1, any_paeth));
@@ -280,8 +317,18 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
                 }
                 o = make_uint4(os[0], os[1], os[2], os[3]);
             }
-            int nbytes = (int)pitch - 16 * j;
-            store16_partial(out + 16 * (uint64_t)j, o, nbytes);
+            if (WAVE_OUT == 0) {
+                int nbytes = (int)pitch - 16 * j;
+                store16_partial(out + 16 * (uint64_t)j, o, nbytes);
+            } else {
+                oring[j % WAVE_OUTM][lane] = o;
+                if ((j + 1) % WAVE_OUTM == 0 || j + 1 == nchunk) {
+                    const int j0 = j - j % WAVE_OUTM;
+#pragma unroll
+                    for (int k = 0; k < WAVE_OUT; ++k)
+                        if (j0 + k <= j) store16_partial(out + 16 * (uint64_t)(j0 + k), oring[k][lane], (int)pitch - 16 * (j0 + k));
+                }
+            }
             mine = o;
             if (publish && (((j + 1) % WAVE_PUBLISH) == 0 || j + 1 == nchunk)) {
                 __threadfence();
@@ -295,8 +342,9 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
 
 __global__ void __launch_bounds__(WAVE_WARPS * 32) unfilter_wave_kernel(WaveParams p)
 {
-    __shared__ uint4 rings[WAVE_WARPS][WAVE_DEPTH][32];   // [warp][slot][lane]: conflict-free 16-byte accesses
-    uint4 (*ring)[32] = rings[threadIdx.x >> 5];
+    PNGB200_DYN_SMEM(wave_smem);   // [warp][slot][lane] input rings, then [warp][slot][lane] output rings: conflict-free 16-byte accesses
+    uint4 (*ring)[32]  = reinterpret_cast<uint4 (*)[32]>(wave_smem) + (threadIdx.x >> 5) * WAVE_DEPTH;
+    uint4 (*oring)[32] = reinterpret_cast<uint4 (*)[32]>(wave_smem) + WAVE_WARPS * WAVE_DEPTH + (threadIdx.x >> 5) * WAVE_OUT;
     const unsigned lane = lane_id();
     for (;;) {
         uint32_t t = 0;
@@ -316,12 +364,12 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) unfilter_wave_kernel(WavePara
         uint32_t*      prev  = band == 0 ? nullptr : p.progress + t - 1;
         uint32_t*      mine  = band + 1 < nband ? p.progress + t : nullptr;
         switch (job.bpp) {
-        case 1: wave_band<1>(job, band, prev, mine, ring, p.hist); break;
-        case 2: wave_band<2>(job, band, prev, mine, ring, p.hist); break;
-        case 3: wave_band<3>(job, band, prev, mine, ring, p.hist); break;
-        case 4: wave_band<4>(job, band, prev, mine, ring, p.hist); break;
-        case 6: wave_band<6>(job, band, prev, mine, ring, p.hist); break;
-        default: wave_band<8>(job, band, prev, mine, ring, p.hist); break;
+        case 1: wave_band<1>(job, band, prev, mine, ring, oring, p.hist); break;
+        case 2: wave_band<2>(job, band, prev, mine, ring, oring, p.hist); break;
+        case 3: wave_band<3>(job, band, prev, mine, ring, oring, p.hist); break;
+        case 4: wave_band<4>(job, band, prev, mine, ring, oring, p.hist); break;
+        case 6: wave_band<6>(job, band, prev, mine, ring, oring, p.hist); break;
+        default: wave_band<8>(job, band, prev, mine, ring, oring, p.hist); break;
         }
     }
 }
