@@ -80,7 +80,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-batch", type=int, default=0, help="images per GPU in the host-buffer leg (0 = auto: whole batch if <= 110 GB pinned)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-gib", type=int, default=48, help="pinned host staging per rank for the end-to-end leg (GiB, upper bound)")
+    ap.add_argument("--e2e-gib", type=int, default=0, help="pinned host staging per rank for the end-to-end leg (GiB, upper bound; "
+                    "0 = 96 on one GPU -- the whole 444-image batch -- and 24 per rank under torchrun)")
     ap.add_argument("--e2e-api", choices=["idat", "files"], default="idat",
                     help="host leg through pngb200_decode_batch (IDAT payloads) or pngb200_png_decode_batch (whole PNG files, "
                          "65544-byte IDAT chunks: chunk CRC-32 and IDAT gather on the device)")
@@ -371,10 +372,11 @@ def main():
     if not args.no_e2e:
         import psutil
         per_image = storage_bytes + max(len(it["idat"]) for it in items)
-        # Pinned host staging per rank: min(48 GiB, 30 % of the host memory that is free / ranks), decided ONCE
+        # Pinned host staging per rank: min(96 GiB alone / 24 GiB per rank under torchrun, 30 % of the free host memory / ranks), decided ONCE
         # on rank 0 and broadcast, so that every rank times the same sub-batch and 8 ranks cannot pin the box
         # to death (r01 lost its 8-GPU run to 94 GB of pinned memory per rank)
-        budget = min(args.e2e_gib << 30, int(0.3 * psutil.virtual_memory().available / max(world, 1)))
+        gib = args.e2e_gib or (96 if world == 1 else 24)
+        budget = min(gib << 30, int(0.3 * psutil.virtual_memory().available / max(world, 1)))
         EB = max(8, min(B, args.e2e_batch or B, budget // per_image))
         if world > 1:
             eb = torch.tensor([EB], dtype=torch.int64, device="cuda")

@@ -84,7 +84,8 @@ struct ClShared {
     uint32_t     adler_a[WV_WARPS], adler_b[WV_WARPS];
     uint32_t     exc[WV_WARPS], valid[WV_WARPS];
     uint32_t     last, term, anomaly, ticket;
-    uint32_t     cut_pos, cut_out;              // a cut wave: bit position of the first token not emitted, bytes emitted
+    uint32_t     cut_pos, cut_out;
+    uint32_t     hdr_mode, hdr_rel, hdr_ok, hdr_end, hdr_count;   // block header hand-over (see cl_header_preamble)              // a cut wave: bit position of the first token not emitted, bytes emitted
     uint64_t     cyc[12], tick;
     uint64_t     pf_bar;
     WvHeader     hdr;
@@ -193,6 +194,81 @@ __device__ __forceinline__ void cells_copy(cellp_t ch, uint32_t j, uint32_t run,
     for (; k < run; ++k) sts16(to + 2 * k, code + k);
 }
 
+// ---- block header: the code lengths of a dynamic block, decoded by the whole CTA ----
+// wv_fast_header leaves the ~300 code-length symbols of a dynamic header to one lane (a dependent chain of table
+// look-ups: ~100 cycles per symbol, ~25 K cycles per block with seven warps waiting).  Here the part in front of them
+// (block type, counts, the code-length code and its table) stays with warp 0, then
+//   1. every thread decodes the symbol that WOULD start at each of its bit positions (all positions the lengths can
+//      occupy, <= CL_HDR_POS): advance, number of lengths it stands for, their value -> one word per position;
+//   2. one thread follows the chain of those words from the first position (one shared-memory load per symbol on
+//      the critical path, nothing else) and lists the symbols it passes with their output index;
+//   3. every thread expands its part of that list into the length array.
+// Anything irregular -- an invalid code, a repeat without a predecessor, too many lengths, a header that runs past
+// the staged words or the input -- makes the caller run parse_block_header, which owns the reference's error semantics
+// (Stream.readBlockMetadata / readBlockTables, LZ77.InflatorBuffers.Stream.swift:59-263).
+constexpr uint32_t CL_HDR_POS = 4480;   // 316 lengths x (7-bit code + 7 extra bits) at most, rounded up
+
+// warp 0.  Returns 0: use the slow parser; 1: `out` is complete (stored or fixed block); 2: dynamic block, the meta table
+// is built and the code lengths start at staged bit `rel_out`
+template <class Shared>
+__device__ int cl_header_preamble(Shared& sh, uint64_t hbase_bit, uint64_t pos, uint64_t total_bits, int lane, WvHeader& out,
+                                  uint32_t& rel_out)
+{
+    const uint32_t* const W = sh.words;
+    auto get = [&](uint32_t rel, uint32_t n) -> uint32_t {
+        const uint32_t w = rel >> 5;
+        const uint32_t v = __funnelshift_r(W[w], W[w + 1], rel & 31u);
+        return n >= 32 ? v : v & ((1u << n) - 1u);
+    };
+    uint32_t rel = (uint32_t)(pos - hbase_bit);
+    if (pos + 3 > total_bits) return 0;
+    const uint32_t h3 = get(rel, 3);
+    rel += 3;
+    out.status = PNGB200_OK;
+    out.final = (int32_t)(h3 & 1u);
+    out.type = (int32_t)(h3 >> 1);
+    out.stored = 0;
+    out.nlit = out.ndist = 0;
+    if (out.type == 3) return 0;
+    if (out.type == 0) {
+        const uint64_t boundary = (pos + 3 + 7) & ~(uint64_t)7;
+        if (boundary + 32 > total_bits) return 0;
+        const uint32_t v = get((uint32_t)(boundary - hbase_bit), 32);
+        const uint32_t l = v & 0xffffu, m = v >> 16;
+        if (l != (~m & 0xffffu)) return 0;
+        out.stored = l;
+        out.pos = boundary + 32;
+        return 1;
+    }
+    uint8_t* const lens = sh.ser.lens;
+    if (out.type == 1) {
+        for (int k = lane; k < 320; k += 32) lens[k] = k < 144 ? 8 : k < 256 ? 9 : k < 280 ? 7 : k < 288 ? 8 : 5;
+        out.nlit = 288;
+        out.ndist = 32;
+        out.pos = pos + 3;
+        __syncwarp();
+        return 1;
+    }
+    if (pos + 17 > total_bits) return 0;
+    const uint32_t v = get(rel, 14);
+    rel += 14;
+    const int nlit = 257 + (int)(v & 31u), ndist = 1 + (int)((v >> 5) & 31u), nclen = 4 + (int)(v >> 10);
+    if (nlit > 286) return 0;
+    if (lane < 19) lens[lane] = 0;
+    __syncwarp();
+    if (lane < nclen) lens[c_clen_order[lane]] = (uint8_t)get(rel + 3u * (uint32_t)lane, 3);
+    rel += 3u * (uint32_t)nclen;
+    __syncwarp();
+    build_table<META_ROOT, META_CAP>(sh.ser.meta, lens, 19, ALPHA_META, &sh.ser.scratch, lane, 32);
+    if (sh.ser.scratch.status) return 0;
+    __syncwarp();
+    if (rel + CL_HDR_POS + 64 > 32u * WV_HDR_WORDS) return 0;   // (cannot happen: the header starts in the first staged word)
+    out.nlit = nlit;
+    out.ndist = ndist;
+    rel_out = rel;
+    return 2;
+}
+
 __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kernel(WvParams P)
 {
     PNGB200_DYN_SMEM(cl_smem);
@@ -294,17 +370,86 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                 const uint64_t hbase = br.pos >> 5;
                 for (uint32_t k = t; k < WV_HDR_WORDS; k += WV_THREADS) sh.words[k] = br.load_word(hbase + k);
                 __syncthreads();
+                auto slow_header = [&](WvHeader& h) {   // warp 0: the general parser, exact error semantics
+                    int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
+                    uint32_t stored0 = 0;
+                    StagedReader sr;
+                    sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
+                    int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
+                    h = WvHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                };
                 if (warp == 0) {
                     WvHeader h;
-                    if (!wv_fast_header(sh, hbase << 5, br.pos, br.total_bits, (int)lane, h)) {
-                        int      type0 = 0, final0 = 0, nlit0 = 0, ndist0 = 0;
-                        uint32_t stored0 = 0;
-                        StagedReader sr;
-                        sr.init(sh.words, hbase << 5, br.total_bits, br.pos);
-                        int st0 = parse_block_header(sr, &sh.ser, r, (int)lane, &type0, &final0, &stored0, &nlit0, &ndist0);
-                        h = WvHeader{st0, type0, final0, nlit0, ndist0, stored0, sr.pos};
+                    uint32_t rel = 0;
+                    const int mode = cl_header_preamble(sh, hbase << 5, br.pos, br.total_bits, (int)lane, h, rel);
+                    if (mode == 0) slow_header(h);
+                    if (lane == 0) {
+                        sh.hdr = h;
+                        sh.hdr_mode = (uint32_t)mode;
+                        sh.hdr_rel = rel;
                     }
-                    if (lane == 0) sh.hdr = h;
+                }
+                __syncthreads();
+                if (sh.hdr_mode == 2) {
+                    // ---- the code lengths of a dynamic block, by the whole CTA (tab[] and the symbol list live in the
+                    //      cell array, which is idle between blocks) ----
+                    const uint32_t rel = sh.hdr_rel;
+                    const int      total_lens = sh.hdr.nlit + sh.hdr.ndist;
+                    const saddr_t  tab = ch, list = ch + 4 * CL_HDR_POS;
+                    const uint32_t* const W = sh.words;
+                    for (uint32_t q = t; q < CL_HDR_POS; q += WV_THREADS) {
+                        const uint32_t at = rel + q;
+                        const uint32_t bits = __funnelshift_r(W[at >> 5], W[(at >> 5) + 1], at & 31u);
+                        const uint32_t e = sh.ser.meta[bits & (META_CAP - 1)];
+                        uint32_t word = 0;                                  // advance 0: not a symbol
+                        if (!(e & E_SPECIAL)) {
+                            const uint32_t len = e & 15u, sym = e >> 16, x = bits >> len;
+                            // advance | lengths it stands for << 8 | value << 16 (0xff: the previous length)
+                            word = sym < 16   ? (len | 1u << 8 | sym << 16)
+                                 : sym == 16 ? ((len + 2u) | (3u + (x & 3u)) << 8 | 0xffu << 16)
+                                 : sym == 17 ? ((len + 3u) | (3u + (x & 7u)) << 8)
+                                             : ((len + 7u) | (11u + (x & 127u)) << 8);
+                        }
+                        sts32(tab + 4 * q, word);
+                    }
+                    __syncthreads();
+                    if (t == 0) {
+                        uint32_t p = 0, have = 0, prev = 0, count = 0, ok = 1;
+                        while (have < (uint32_t)total_lens) {
+                            const uint32_t e = lds32(tab + 4 * p);
+                            const uint32_t adv = e & 0xffu, cnt = (e >> 8) & 0xffu;
+                            uint32_t val = e >> 16;
+                            if (adv == 0 || (val == 0xffu && have == 0) || have + cnt > (uint32_t)total_lens) { ok = 0; break; }
+                            if (val == 0xffu) val = prev;
+                            sts32(list + 4 * count, have | cnt << 9 | val << 17);
+                            ++count;
+                            prev = val;
+                            have += cnt;
+                            p += adv;
+                            if (p >= CL_HDR_POS) { ok = 0; break; }
+                        }
+                        const uint64_t end = (hbase << 5) + rel + p;
+                        if (end > br.total_bits) ok = 0;
+                        sh.hdr_ok = ok;
+                        sh.hdr_count = count;
+                        sh.hdr.pos = end;
+                    }
+                    __syncthreads();
+                    if (sh.hdr_ok) {
+                        const uint32_t count = sh.hdr_count;
+                        for (uint32_t i = t; i < count; i += WV_THREADS) {
+                            const uint32_t e = lds32(list + 4 * i);
+                            const uint32_t at = e & 0x1ffu, cnt = (e >> 9) & 0xffu, val = e >> 17;
+                            for (uint32_t k = 0; k < cnt; ++k) sh.ser.lens[at + k] = (uint8_t)val;
+                        }
+                    } else if (warp == 0) {
+                        WvHeader h;
+                        slow_header(h);
+                        if (lane == 0) sh.hdr = h;
+                    }
+#if defined(PNGB200_EMU) && defined(WV_PROFILE)
+                    if (t == 0) wv_profile().thread_iters[5] += sh.hdr_ok ? 1 : 0, wv_profile().thread_iters[6] += sh.hdr_ok ? 0 : 1;
+#endif
                 }
             }
             __syncthreads();

@@ -2,8 +2,8 @@
 # one GPU window of round-2 experiments (runs on the GPU box): correctness of the cell engine, engine and unfilter
 # variants on the default bench, ncu captures.  Results in gpurun_out/c4_*.
 mkdir -p gpurun_out
-(timeout 240 python -m pytest tests/test_gpu_decode.py -q -x -k "cells or unfilter or pngsuite_all" 2>&1 | tail -4) > gpurun_out/c4_tests.log 2>&1
-tools/gpu_exp.sh c4 main:6 main:0 ub84:0 ub48:0 ub88:0 stage1:6 nostage:6 c2:6 > gpurun_out/c4_summary.txt 2>&1
+(timeout 240 python -m pytest tests/test_gpu_decode.py tests/test_gpu_zz_cells.py -q -x -k "cells or unfilter or pngsuite_all" 2>&1 | tail -4) > gpurun_out/c4_tests.log 2>&1
+tools/gpu_exp.sh c4 main:6 ph:6 main:0 ub84:0 ub48:0 ub88:0 stage1:6 nostage:6 c2:6 > gpurun_out/c4_summary.txt 2>&1
 cat gpurun_out/c4_tests.log gpurun_out/c4_summary.txt
 N="python bench.py --workload 1080p-rgba8 --batch 444 --steps 1 --warmup 1 --no-e2e --no-cpu"
 (timeout 240 ncu --set full --import-source on --clock-control none -k regex:inflate_cells -c 1 -f -o gpurun_out/c4_cells $N --inflate-mode 6 > gpurun_out/c4_ncu1.log 2>&1)
