@@ -381,7 +381,11 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                 if (warp == 0) {
                     WvHeader h;
                     uint32_t rel = 0;
+#ifdef CL_SERIAL_HEADER   // (tuning builds: the code lengths by one lane, as in inflate_wave_kernel)
+                    const int mode = wv_fast_header(sh, hbase << 5, br.pos, br.total_bits, (int)lane, h) ? 1 : 0;
+#else
                     const int mode = cl_header_preamble(sh, hbase << 5, br.pos, br.total_bits, (int)lane, h, rel);
+#endif
                     if (mode == 0) slow_header(h);
                     if (lane == 0) {
                         sh.hdr = h;

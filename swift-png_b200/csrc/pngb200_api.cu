@@ -796,6 +796,7 @@ pngb200_ctx* pngb200_ctx_create(int device)
     pngb200_ctx* ctx = new pngb200_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* v = getenv("PNGB200_CELLS_AUTO")) ctx->cells_auto = atoi(v) != 0;   // tuning override, read once per context
     DeviceGuard guard(device);
     if (cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)) != cudaSuccess) {
         set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(DfShared));
