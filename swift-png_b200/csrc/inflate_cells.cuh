@@ -102,7 +102,6 @@ inline void     sts16(saddr_t a, uint32_t v) { *(volatile uint16_t*)a = (uint16_
 inline uint32_t lds16(saddr_t a) { return *(volatile uint16_t*)a; }
 inline void     sts32(saddr_t a, uint32_t v) { *(volatile uint32_t*)a = v; }
 inline void     reds_or(saddr_t a, uint32_t v) { *(volatile uint32_t*)a |= v; }
-inline saddr_t  opaque(saddr_t a) { return a; }
 #else
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v)
 {
@@ -121,11 +120,6 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
 __device__ __forceinline__ void reds_or(uint32_t a, uint32_t v)
 {
     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t opaque(uint32_t a)   // a value the compiler cannot rematerialise: it stays in a register
-{
-    asm volatile("" : "+r"(a));
-    return a;
 }
 #endif
 typedef saddr_t cellp_t;   // shared-window address of cells[0]

@@ -110,8 +110,14 @@ __device__ __forceinline__ void par_decode_count(const ParShared& sh, uint32_t s
                                                  uint32_t& flags)
 {
     FastBits b;
+#ifdef PAR_OPAQUE_BASE
+    const saddr_t sb = opaque(smem_addr(&sh));
+    b.init(sb + offsetof(ParShared, words), start);
+    const saddr_t lit = sb + offsetof(ParShared, ser) + offsetof(SerialShared, lit), dst = sb + offsetof(ParShared, ser) + offsetof(SerialShared, dist);
+#else
     b.init(smem_addr(sh.words), start);
     const saddr_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
+#endif
     nout  = 0;
     ncopy = 0;
     flags = 0;
@@ -465,8 +471,14 @@ __device__ __forceinline__ void inflate_parallel_body(ParParams P)
                     uint32_t* const U      = in_hbm ? gbitmap : sh.bitmap;
                     if (t < nvalid) {
                         FastBits b;
+#ifdef PAR_OPAQUE_BASE
+                        const saddr_t sb = opaque(smem_addr(&sh));
+                        b.init(sb + offsetof(ParShared, words), my_start);
+                        const saddr_t lit = sb + offsetof(ParShared, ser) + offsetof(SerialShared, lit), dst = sb + offsetof(ParShared, ser) + offsetof(SerialShared, dist);
+#else
                         b.init(smem_addr(sh.words), my_start);
                         const saddr_t lit = smem_addr(sh.ser.lit), dst = smem_addr(sh.ser.dist);
+#endif
                         uint32_t o = o_start;
                         uint32_t mw = o_start >> 5, mbits = 0;   // pending unresolved-bit word
                         while (b.pos < limit) {

@@ -155,6 +155,7 @@ typedef uintptr_t saddr_t;
 inline uint32_t lds32(saddr_t addr) { return *(const uint32_t*)addr; }
 inline uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len);
 inline saddr_t smem_addr(const void* p) { return (uintptr_t)p; }
+inline saddr_t opaque(saddr_t a) { return a; }
 inline uint32_t bmsk(uint32_t pos, uint32_t width)   // PTX bmsk.clamp.b32: `width` one bits starting at bit `pos`
 {
     pos &= 0xff; width &= 0xff;
@@ -184,6 +185,13 @@ __device__ __forceinline__ uint32_t bfe32(uint32_t x, uint32_t pos, uint32_t len
     return (x >> pos) & bmsk(0, len);
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// a value the compiler cannot rematerialise: it stays in a register (a shared-window address is otherwise rebuilt from
+// SR_CgaCtaId wherever registers are short -- an S2R at the top of a decode loop, ncu r02)
+__device__ __forceinline__ uint32_t opaque(uint32_t a)
+{
+    asm volatile("" : "+r"(a));
+    return a;
+}
 #endif
 
 // ---- bulk asynchronous copy (TMA, 1-D) global -> shared memory, completion on an mbarrier ----

@@ -641,13 +641,45 @@ int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
     band_base.push_back((uint32_t)bands);
     if (bands >= (1ull << 31)) return set_error(ctx, PNGB200_ERR_BAD_ARGUMENT, "batch too large");
     if (!fast.empty()) {
+        // Tickets go out band level by band level (see WaveParams): jobs sorted by band count, descending; level_start[b] =
+        // tickets in front of level b.  (Images of more than 4096 bands -- 131072 rows -- keep the image-major order.)
+        std::vector<uint32_t> level_start;
+        {
+            std::vector<uint32_t> idx(fast.size());
+            for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
+            auto nb = [&](uint32_t i) { return (fast[i].height + 31) / 32; };
+            std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return nb(a) > nb(b); });
+            const uint32_t maxb = nb(idx[0]);
+#ifndef PNGB200_WAVE_IMAGE_MAJOR   // (tuning builds: the round-2a order)
+            if (maxb <= 4096) {
+                std::vector<ImageJob> sorted(fast.size());
+                for (size_t i = 0; i < idx.size(); ++i) sorted[i] = fast[idx[i]];
+                fast.swap(sorted);
+                uint64_t at = 0;
+                for (size_t i = 0; i < fast.size(); ++i) {
+                    band_base[i] = (uint32_t)at;
+                    at += (fast[i].height + 31) / 32;
+                }
+                level_start.assign(maxb + 1, 0);
+                size_t alive = fast.size();          // images with more than b bands: a prefix of the sorted list
+                for (uint32_t b = 0; b < maxb; ++b) {
+                    while (alive && (fast[alive - 1].height + 31) / 32 <= b) --alive;
+                    level_start[b + 1] = level_start[b] + (uint32_t)alive;
+                }
+            }
+#else
+            (void)maxb;
+#endif
+        }
         size_t jb = sizeof(ImageJob) * fast.size(), bb = sizeof(uint32_t) * band_base.size();
-        size_t off_bb = align_up(jb, 256), off_pr = align_up(off_bb + bb, 256);
+        size_t lb = sizeof(uint32_t) * level_start.size();
+        size_t off_bb = align_up(jb, 256), off_ls = align_up(off_bb + bb, 256), off_pr = align_up(off_ls + lb, 256);
         size_t total = align_up(off_pr + sizeof(uint32_t) * (bands + 1), 8) + 8 * sizeof(unsigned long long);
         CU(ctx->h_imgjobs.reserve(off_pr));
         CU(ctx->d_imgjobs.reserve(total));
         memcpy(ctx->h_imgjobs.p, fast.data(), jb);
         memcpy((char*)ctx->h_imgjobs.p + off_bb, band_base.data(), bb);
+        if (lb) memcpy((char*)ctx->h_imgjobs.p + off_ls, level_start.data(), lb);
         CU(cudaMemcpyAsync(ctx->d_imgjobs.p, ctx->h_imgjobs.p, off_pr, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync((char*)ctx->d_imgjobs.p + off_pr, 0, sizeof(uint32_t) * (bands + 1), ctx->stream));
         WaveParams p;
@@ -660,6 +692,8 @@ int run_unfilter(pngb200_ctx* ctx, const std::vector<UnfilterItem>& items)
         ctx->d_hist = p.hist;
         p.njobs = (uint32_t)fast.size();
         p.total_bands = (uint32_t)bands;
+        p.level_start = (const uint32_t*)((char*)ctx->d_imgjobs.p + off_ls);
+        p.levels = level_start.empty() ? 0u : (uint32_t)level_start.size() - 1;
         unsigned grid = (unsigned)std::min<uint64_t>((bands + WAVE_WARPS - 1) / WAVE_WARPS,
                                                      (uint64_t)ctx->sm_count * 8);
         unfilter_wave_kernel<<<grid, WAVE_WARPS * 32, WAVE_SMEM, ctx->stream>>>(p);

@@ -115,6 +115,14 @@ struct WaveParams {
     uint32_t*       ticket;
     uint32_t        njobs;
     uint32_t        total_bands;
+    // Ticket order.  levels == 0: image after image (ticket = band_base[image] + band).  Otherwise band LEVEL after
+    // level: jobs[] is sorted by band count (descending), level_start[b] = tickets in front of level b = sum over
+    // b' < b of the images that have more than b' bands, and ticket level_start[b] + r is band b of image r.  A band
+    // follows the band above it by ~40 steps, so of one image's bands only duration / 40 can be busy at a time; handed
+    // out image by image the resident warps hold ALL bands of a few images and most of them wait for their turn (ncu
+    // r02: 31 % of the samples in that wait); handed out level by level they hold a few bands of every image.
+    const uint32_t* level_start;   // [levels + 1]
+    uint32_t        levels;
     unsigned long long* hist;   // [6]: scanlines per filter type 0..4, [5] = invalid filter bytes (the reference's
                                 // -DDUMP_FILTERED_SCANLINES view of a decode, PNG.Decoder.swift:96-98,128); may be null
 };
@@ -127,6 +135,24 @@ constexpr int WAVE_WARPS   = PNGB200_WAVE_WARPS;
 #define PNGB200_WAVE_PUBLISH 8
 #endif
 constexpr int WAVE_PUBLISH = PNGB200_WAVE_PUBLISH;  // publish progress every this many chunks
+#ifndef PNGB200_WAVE_POLL_NS
+#define PNGB200_WAVE_POLL_NS 64
+#endif
+// A band that has caught up with the band above waits until that band is WAVE_LAG chunks ahead again, not just one:
+// right behind its producer a band pays two L2 round trips per chunk (the progress word, then the row-above chunk,
+// which cannot be prefetched before it is published) -- ncu r02: 31 % of all samples in that poll, 2.5 us per step.
+#ifndef PNGB200_WAVE_LAG
+#define PNGB200_WAVE_LAG 1
+#endif
+constexpr uint32_t WAVE_LAG = PNGB200_WAVE_LAG;
+// Lane 0's "previous row" is the last row of the band above, written by another warp.  Fetched one step ahead in
+// registers (round 2a) its L2 round trip sat on the warp's critical path at every step (ncu r02b: 38 % of the samples
+// on the first use of that value).  WAVE_ABOVE: lane 0 stages the aligned chunks of that row through a 32-slot ring with
+// the same cp.async groups as its own row, two blocks of 8 ahead, as far as the band above has published them.
+#ifndef PNGB200_WAVE_ABOVE
+#define PNGB200_WAVE_ABOVE 0
+#endif
+constexpr int WAVE_ABOVE = PNGB200_WAVE_ABOVE;
 
 // Asynchronous staging of a lane's own row (cp.async = LDGSTS: global -> shared memory without a register in
 // between).  Every lane keeps a private ring of WAVE_DEPTH aligned 16-byte chunks of its row in shared memory and
@@ -143,7 +169,7 @@ constexpr int WAVE_BURST = PNGB200_WAVE_BURST;                 // chunks per ref
 constexpr int WAVE_DEPTH = WAVE_BURST == 1 ? 8 : 3 * WAVE_BURST;   // ring slots per lane
 constexpr int WAVE_OUT   = WAVE_BURST == 1 ? 0 : WAVE_BURST;   // output chunks collected per lane before they are stored
 constexpr int WAVE_OUTM  = WAVE_OUT ? WAVE_OUT : 1;           // (modulus that is never zero)
-constexpr size_t WAVE_SMEM = sizeof(uint4) * 32 * (size_t)WAVE_WARPS * (WAVE_DEPTH + (WAVE_OUT ? WAVE_OUT : 0));
+constexpr size_t WAVE_SMEM = sizeof(uint4) * 32 * (size_t)WAVE_WARPS * (WAVE_DEPTH + (WAVE_OUT ? WAVE_OUT : 0) + (WAVE_ABOVE ? 1 : 0));
 __device__ __forceinline__ void cp_async16(uint4* smem, const uint4* gmem)
 {
 #ifdef PNGB200_EMU
@@ -168,7 +194,7 @@ __device__ __forceinline__ void cp_async_wait()   // at most N of this thread's 
 
 template <int BPP>
 __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_prev, uint32_t* prog_mine, uint4 (*ring)[32],
-                          uint4 (*oring)[32], unsigned long long* hist)
+                          uint4 (*oring)[32], uint4* aring, unsigned long long* hist)
 {
     const unsigned lane   = lane_id();
     const uint32_t y      = band * 32 + lane;
@@ -209,6 +235,11 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
     uint32_t seen = 0;
     uint4    upn = make_uint4(0, 0, 0, 0);  // lane 0: the chunk of the row above for the next step
     bool     upn_ok = false;
+    // lane 0, WAVE_ABOVE: aligned 16-byte chunks of the row above; chunk c lives in aring[c & 31]
+    const uint32_t ma    = above != nullptr ? (uint32_t)((uintptr_t)above & 15) : 0u;
+    const uint4*   aq    = (const uint4*)(above - ma);
+    const uint32_t nqa   = (ma + pitch + 15) >> 4;
+    uint32_t       a_cur = 0, a_prev = 0;   // aligned chunks issued so far / as of the block boundary before this one
     // input chunk k of my row is cp.async group k of this thread: WAVE_DEPTH groups are opened here, one more per
     // step, so when chunk j is consumed the groups up to j + 1 must have landed = at most WAVE_DEPTH - 2 in flight
     if (active) {
@@ -240,13 +271,33 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
             // the band above publishes its last row chunk by chunk; its chunk j + 1 is fetched while chunk j
             // is being used, so the L2 round trip of that load is off the warp's critical path
             up = make_uint4(0, 0, 0, 0);
-            if (active && above != nullptr && j < nchunk) {
+            bool staged_above = false;
+            if (WAVE_ABOVE && WAVE_BURST == 1 && active && above != nullptr && j >= 0 && j < nchunk) {
+                if (j % 8 == 0) {
+                    // once per block of 8: how far has the band above got; issue what it has published of the next
+                    // two blocks (these copies join this step's cp.async group: they have landed 8 steps from now)
+                    a_prev = a_cur;
+                    if (seen < (uint32_t)nchunk) seen = ld_volatile_u32(prog_prev);
+                    const uint32_t avail = seen >= (uint32_t)nchunk ? nqa : seen;   // aligned chunk c is complete once c + 1 <= seen
+                    const uint32_t hi = min(min(avail, (uint32_t)j + 18u), nqa);
+                    for (uint32_t c = a_cur; c < hi; ++c) cp_async16(&aring[c & 31], aq + c);
+                    a_cur = max(a_cur, hi);
+                }
+                if ((uint32_t)j + (ma ? 2u : 1u) <= a_prev) {
+                    const uint4 q0 = aring[j & 31];
+                    up = ma == 0 ? q0 : shift_bytes(q0, aring[(j + 1) & 31], ma);
+                    staged_above = true;
+                    upn_ok = false;
+                }
+            }
+            if (!staged_above && active && above != nullptr && j < nchunk) {
                 if (upn_ok) {
                     up = upn;
                 } else {
-                    while (seen <= (uint32_t)j) {
+                    const uint32_t want = min((uint32_t)j + WAVE_LAG, (uint32_t)nchunk);   // chunks the band above must have published
+                    while (seen < want) {
                         seen = ld_volatile_u32(prog_prev);
-                        if (seen <= (uint32_t)j) __nanosleep(64);
+                        if (seen < want) __nanosleep(PNGB200_WAVE_POLL_NS);
                     }
                     up = load16_any(above + 16 * (uint64_t)j, true);
                 }
@@ -345,31 +396,47 @@ __global__ void __launch_bounds__(WAVE_WARPS * 32) unfilter_wave_kernel(WavePara
     PNGB200_DYN_SMEM(wave_smem);   // [warp][slot][lane] input rings, then [warp][slot][lane] output rings: conflict-free 16-byte accesses
     uint4 (*ring)[32]  = reinterpret_cast<uint4 (*)[32]>(wave_smem) + (threadIdx.x >> 5) * WAVE_DEPTH;
     uint4 (*oring)[32] = reinterpret_cast<uint4 (*)[32]>(wave_smem) + WAVE_WARPS * WAVE_DEPTH + (threadIdx.x >> 5) * WAVE_OUT;
+    uint4* aring = reinterpret_cast<uint4*>(reinterpret_cast<uint4 (*)[32]>(wave_smem) + WAVE_WARPS * (WAVE_DEPTH + WAVE_OUT) + (threadIdx.x >> 5));
     const unsigned lane = lane_id();
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(p.ticket, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= p.total_bands) return;
-        // image owning ticket t: last index with band_base[i] <= t
-        uint32_t lo = 0, hi = p.njobs;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (p.band_base[mid] <= t) lo = mid;
-            else hi = mid;
+        uint32_t lo = 0, band, gidx;
+        if (p.levels) {
+            // level of ticket t: last b with level_start[b] <= t
+            uint32_t hi = p.levels;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (p.level_start[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            band = lo;
+            lo   = t - p.level_start[band];          // image (rank in the sorted job list)
+            gidx = p.band_base[lo] + band;
+        } else {
+            // image owning ticket t: last index with band_base[i] <= t
+            uint32_t hi = p.njobs;
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (p.band_base[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            band = t - p.band_base[lo];
+            gidx = t;
         }
         const ImageJob job   = p.jobs[lo];
-        const uint32_t band  = t - p.band_base[lo];
         const uint32_t nband = p.band_base[lo + 1] - p.band_base[lo];
-        uint32_t*      prev  = band == 0 ? nullptr : p.progress + t - 1;
-        uint32_t*      mine  = band + 1 < nband ? p.progress + t : nullptr;
+        uint32_t*      prev  = band == 0 ? nullptr : p.progress + gidx - 1;
+        uint32_t*      mine  = band + 1 < nband ? p.progress + gidx : nullptr;
         switch (job.bpp) {
-        case 1: wave_band<1>(job, band, prev, mine, ring, oring, p.hist); break;
-        case 2: wave_band<2>(job, band, prev, mine, ring, oring, p.hist); break;
-        case 3: wave_band<3>(job, band, prev, mine, ring, oring, p.hist); break;
-        case 4: wave_band<4>(job, band, prev, mine, ring, oring, p.hist); break;
-        case 6: wave_band<6>(job, band, prev, mine, ring, oring, p.hist); break;
-        default: wave_band<8>(job, band, prev, mine, ring, oring, p.hist); break;
+        case 1: wave_band<1>(job, band, prev, mine, ring, oring, aring, p.hist); break;
+        case 2: wave_band<2>(job, band, prev, mine, ring, oring, aring, p.hist); break;
+        case 3: wave_band<3>(job, band, prev, mine, ring, oring, aring, p.hist); break;
+        case 4: wave_band<4>(job, band, prev, mine, ring, oring, aring, p.hist); break;
+        case 6: wave_band<6>(job, band, prev, mine, ring, oring, aring, p.hist); break;
+        default: wave_band<8>(job, band, prev, mine, ring, oring, aring, p.hist); break;
         }
     }
 }
