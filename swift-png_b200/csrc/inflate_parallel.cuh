@@ -55,6 +55,9 @@ constexpr int      PAR_WARPS        = PAR_THREADS / 32;
 #ifndef PAR_S
 #define PAR_S 256
 #endif
+#ifndef PAR_NO_OPAQUE_BASE
+#define PAR_OPAQUE_BASE 1   // decode loops address shared memory from a base the compiler cannot rebuild from SR_CgaCtaId (r02b: 791 -> 786 ms)
+#endif
 constexpr uint32_t PAR_SUB_BITS     = PAR_S;
 constexpr uint32_t PAR_SUB_WORDS    = PAR_SUB_BITS / 32;
 constexpr uint32_t PAR_WAVE_WORDS   = PAR_THREADS * PAR_SUB_WORDS + 8;

@@ -128,7 +128,7 @@ struct WaveParams {
 };
 
 #ifndef PNGB200_WAVE_WARPS
-#define PNGB200_WAVE_WARPS 8
+#define PNGB200_WAVE_WARPS 4
 #endif
 constexpr int WAVE_WARPS   = PNGB200_WAVE_WARPS;
 #ifndef PNGB200_WAVE_PUBLISH
@@ -153,6 +153,18 @@ constexpr uint32_t WAVE_LAG = PNGB200_WAVE_LAG;
 #define PNGB200_WAVE_ABOVE 0
 #endif
 constexpr int WAVE_ABOVE = PNGB200_WAVE_ABOVE;
+// Every lane asks L2 for the 128-byte line of its row that lies WAVE_L2PF bytes ahead of the chunk it is staging (one
+// prefetch.global.L2 per 8 chunks): lookahead beyond the shared-memory ring without paying for it in resident warps.
+#ifndef PNGB200_WAVE_L2PF
+#define PNGB200_WAVE_L2PF 0
+#endif
+constexpr int WAVE_L2PF = PNGB200_WAVE_L2PF;
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+#ifndef PNGB200_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 
 // Asynchronous staging of a lane's own row (cp.async = LDGSTS: global -> shared memory without a register in
 // between).  Every lane keeps a private ring of WAVE_DEPTH aligned 16-byte chunks of its row in shared memory and
@@ -166,7 +178,10 @@ constexpr int WAVE_ABOVE = PNGB200_WAVE_ABOVE;
 #define PNGB200_WAVE_BURST 1
 #endif
 constexpr int WAVE_BURST = PNGB200_WAVE_BURST;                 // chunks per refill (1: one chunk per step, as in round 2a)
-constexpr int WAVE_DEPTH = WAVE_BURST == 1 ? 8 : 3 * WAVE_BURST;   // ring slots per lane
+#ifndef PNGB200_WAVE_DEPTH1
+#define PNGB200_WAVE_DEPTH1 16
+#endif
+constexpr int WAVE_DEPTH = WAVE_BURST == 1 ? PNGB200_WAVE_DEPTH1 : 3 * WAVE_BURST;   // ring slots per lane
 constexpr int WAVE_OUT   = WAVE_BURST == 1 ? 0 : WAVE_BURST;   // output chunks collected per lane before they are stored
 constexpr int WAVE_OUTM  = WAVE_OUT ? WAVE_OUT : 1;           // (modulus that is never zero)
 constexpr size_t WAVE_SMEM = sizeof(uint4) * 32 * (size_t)WAVE_WARPS * (WAVE_DEPTH + (WAVE_OUT ? WAVE_OUT : 0) + (WAVE_ABOVE ? 1 : 0));
@@ -331,6 +346,7 @@ __device__ void wave_band(const ImageJob& job, uint32_t band, uint32_t* prog_pre
                 // chunk j + WAVE_DEPTH takes the slot chunk j just left (x depends on the loads above: they are done)
                 if (j + WAVE_DEPTH < nq) cp_async16(&ring[j % WAVE_DEPTH][lane], inq + j + WAVE_DEPTH);
                 cp_async_commit();
+                if (WAVE_L2PF && (j & 7) == 0 && j + WAVE_DEPTH + WAVE_L2PF / 16 < nq) prefetch_l2(inq + j + WAVE_DEPTH + WAVE_L2PF / 16);
             }
             uint4 o;
             if (BPP == 4) {
