@@ -1752,31 +1752,64 @@ int pngb200_inflator_push(pngb200_inflator* z, const uint8_t* data, size_t n)
         job->pad_ = 0;
         CU(cudaMemcpyAsync(z->d_job.p, job, sizeof(StreamJob), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(z->d_res.p, 0, sizeof(StreamResult), ctx->stream));
-        inflate_serial_kernel<<<1, 32, 0, ctx->stream>>>(z->d_job.as<StreamJob>(), z->d_res.as<StreamResult>(), nullptr, 1);
-        ctx->launches++;
-        // checksum over everything produced so far (cheap relative to the inflate itself)
-        uint32_t base[2] = {0, (uint32_t)((z->d_out.cap + CK_CHUNK - 1) / CK_CHUNK)};
-        CU(z->d_misc.reserve(sizeof base));
-        CU(z->d_partial.reserve(sizeof(uint64_t) * 2 * std::max<uint32_t>(base[1], 1)));
-        CU(cudaMemcpyAsync(z->d_misc.p, base, sizeof base, cudaMemcpyHostToDevice, ctx->stream));
-        ChecksumParams cp;
-        cp.jobs = z->d_job.as<StreamJob>();
-        cp.results = z->d_res.as<StreamResult>();
-        cp.chunk_base = z->d_misc.as<uint32_t>();
-        cp.partial = z->d_partial.as<uint64_t>();
-        cp.count = 1;
-        cp.total_chunks = base[1];
-        cp.crc_tables = nullptr;
-        if (z->format == PNGB200_FORMAT_GZIP) {
-            if (int rc = ensure_crc_tables(ctx)) return rc;
-            cp.crc_tables = ctx->d_crctab.as<uint32_t>();
+        // A push with a lot of undecoded input goes through the intra-stream parallel kernel (one CTA: ~25 x the
+        // lock-step warp); short ones, and everything irregular inside it, through the serial decoder.  Both resume
+        // at the last completed block boundary.
+        const uint64_t pending = z->input.size() - std::min<uint64_t>(z->input.size(), z->resume_bit >> 3);
+        if (pending >= (64u << 10)) {
+            const uint64_t bitmap_words = wv_bitmap_words(job->dst_cap);
+            const uint64_t stride = wv_scratch_stride(bitmap_words);
+            const size_t   need = (size_t)stride + 256;
+            if (need > ctx->d_scratch.cap || stride != ctx->scratch_stride) {   // (same convention as run_inflate: bitmaps start zeroed)
+                CU(ctx->d_scratch.reserve(need));
+                CU(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, ctx->stream));
+                ctx->scratch_stride = stride;
+            }
+            uint32_t* ticket = (uint32_t*)((char*)ctx->d_scratch.p + (size_t)stride);
+            CU(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), ctx->stream));
+            WvParams pp;
+            pp.bitmap_words = bitmap_words;
+            pp.scratch_stride = stride;
+            pp.ticket = ticket;
+            pp.jobs = z->d_job.as<StreamJob>();
+            pp.results = z->d_res.as<StreamResult>();
+            pp.order = nullptr;
+            pp.scratch = ctx->d_scratch.as<uint8_t>();
+            pp.count = 1;
+            inflate_wave_kernel<<<1, WV_THREADS, sizeof(WvShared), ctx->stream>>>(pp);
+        } else {
+            inflate_serial_kernel<<<1, 32, 0, ctx->stream>>>(z->d_job.as<StreamJob>(), z->d_res.as<StreamResult>(), nullptr, 1);
         }
-        checksum_chunk_kernel<<<base[1], CK_THREADS, 0, ctx->stream>>>(cp);
-        checksum_fold_kernel<<<1, 32, 0, ctx->stream>>>(cp);
-        ctx->launches += 2;
+        ctx->launches++;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(z->h_res.p, z->d_res.p, sizeof(StreamResult), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        // The stream checksum is only due when the trailer has been read: ONE pass over the output at the end of the
+        // stream, not one per push (round 1 re-checksummed everything produced so far on every push).
+        if (z->h_res.as<StreamResult>()->trailer_seen && !z->h_res.as<StreamResult>()->ck_done) {
+            uint32_t base[2] = {0, (uint32_t)((z->d_out.cap + CK_CHUNK - 1) / CK_CHUNK)};
+            CU(z->d_misc.reserve(sizeof base));
+            CU(z->d_partial.reserve(sizeof(uint64_t) * 2 * std::max<uint32_t>(base[1], 1)));
+            CU(cudaMemcpyAsync(z->d_misc.p, base, sizeof base, cudaMemcpyHostToDevice, ctx->stream));
+            ChecksumParams cp;
+            cp.jobs = z->d_job.as<StreamJob>();
+            cp.results = z->d_res.as<StreamResult>();
+            cp.chunk_base = z->d_misc.as<uint32_t>();
+            cp.partial = z->d_partial.as<uint64_t>();
+            cp.count = 1;
+            cp.total_chunks = base[1];
+            cp.crc_tables = nullptr;
+            if (z->format == PNGB200_FORMAT_GZIP) {
+                if (int rc = ensure_crc_tables(ctx)) return rc;
+                cp.crc_tables = ctx->d_crctab.as<uint32_t>();
+            }
+            checksum_chunk_kernel<<<base[1], CK_THREADS, 0, ctx->stream>>>(cp);
+            checksum_fold_kernel<<<1, 32, 0, ctx->stream>>>(cp);
+            ctx->launches += 2;
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(z->h_res.p, z->d_res.p, sizeof(StreamResult), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
         const StreamResult r = *z->h_res.as<StreamResult>();
         // remember the last completed block boundary: the next run resumes there
         z->phase = r.phase;

@@ -266,6 +266,44 @@ def test_streaming_inflator(pngb200, ctx, orc):
     z.close()
 
 
+def test_streaming_inflator_idat_sized_pushes(pngb200, ctx, orc):
+    """a 6 MB stream pushed in 65544-byte slices (the reference's IDAT chunk size), zlib and gzip: big pushes run through the
+    intra-stream parallel kernel from the last block boundary, the checksum pass runs once, when the trailer has been read"""
+    import gzip as gz
+    data = (corpus.make("photo", 1024, 768, 5).tobytes() * 2)[: 6_000_000]
+    for fmt, comp, check in ((pngb200.FORMAT_ZLIB, zlib.compress(data, 6), zlib.adler32(data)),
+                             (pngb200.FORMAT_GZIP, gz.compress(data, 6), zlib.crc32(data))):
+        z = pngb200.Inflator(ctx, fmt)
+        launches0 = ctx.launches
+        out, pushes, status = b"", 0, None
+        for at in range(0, len(comp), 65544):
+            status = z.push(comp[at:at + 65544])
+            pushes += 1
+            while True:
+                row = z.pull(4097)
+                if row is None:
+                    break
+                out += row
+        assert status == pngb200.OK
+        out += z.pull_all()
+        assert out == data
+        assert ctx.launches - launches0 <= pushes * 3 // 2 + 6, (ctx.launches - launches0, pushes)   # ~one decode launch per push + one checksum pass (round 1: three per push)
+        z.close()
+    # a corrupted byte in the middle: the status is the oracle's
+    bad = bytearray(zlib.compress(data, 6))
+    bad[len(bad) // 2] ^= 0x10
+    z = pngb200.Inflator(ctx, pngb200.FORMAT_ZLIB)
+    ost = orc.inflate(bytes(bad), orc.ZLIB, len(data))[0]
+    got = None
+    try:
+        for at in range(0, len(bad), 65544):
+            got = z.push(bytes(bad[at:at + 65544]))
+    except pngb200.PNGB200Error as e:
+        got = e.status
+    assert got == ost
+    z.close()
+
+
 def test_decode_reference_encoded_streams_large_blocks(pngb200, ctx, orc):
     """streams exactly as the reference's encoder emits them (level 9: dynamic blocks of 2047, 4095,
     ... bytes; level 4: <= 2047 terms per block) produced by our bit-exact GPU encoder, decoded by
