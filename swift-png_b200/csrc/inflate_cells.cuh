@@ -33,7 +33,11 @@
 // idle threads, not repeated speculation.  Irregular input (invalid symbol on the chain, truncation, output
 // overflow, a distance reaching in front of the output) goes to the serial decoder as before.
 //
-// Symbolic segment jobs (several CTAs per stream) stay with inflate_wave_kernel.
+// Segment jobs (several CTAs per stream, StreamJob.symbolic): the output is 16-bit symbols in HBM, exactly as
+// inflate_wave_kernel writes them (a byte, or the marker 0x8000 | index into the 32 KiB window in front of the segment).
+// Cells are already symbolic inside a wave; for a segment the store phase keeps them symbolic across waves: a window cell
+// becomes the symbol stored at that position earlier (a marker travels through copies like any other symbol), or a marker
+// when the position lies in front of the segment.
 //
 // Replaces the reference's serial token loop Stream.readBlock(with:) and InflatorOut.expand
 // (Sources/LZ77/Inflator/LZ77.InflatorBuffers.Stream.swift:266-381, LZ77.InflatorOut.swift:124-140),
@@ -309,11 +313,13 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
         uint32_t phase  = (uint32_t)job.phase;
         uint64_t resume_bit = job.start_bit, resume_out = job.start_out;
         uint8_t* const dst = job.dst;
+        const bool     sym = job.symbolic != 0;       // segment: dst is uint16_t[dst_cap]
+        uint16_t* const dst16 = reinterpret_cast<uint16_t*>(job.dst);
         bool fallback = false;
         bool     pf_pending = false;
         uint64_t pf_first = 0;
         uint32_t nsub = WV_THREADS;             // subsequences the next wave speculates on
-        const bool adler_on = job.start_out == 0;
+        const bool adler_on = job.start_out == 0 && !sym;
         uint32_t   s1 = 1, s2 = 0;
         uint64_t   pend_len = 0;
         bool       pend = false;
@@ -466,7 +472,8 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                 if (!br.have(8 * (uint64_t)stored)) { st = PNGB200_NEED_MORE_INPUT; break; }
                 if (out + stored > job.dst_cap) { st = fail(r, PNGB200_ERR_OUTPUT_CAPACITY); break; }
                 const uint8_t* s = job.src + (br.at() >> 3);
-                for (uint32_t k = t; k < stored; k += WV_THREADS) dst[out + k] = s[k];
+                if (sym) for (uint32_t k = t; k < stored; k += WV_THREADS) dst16[out + k] = s[k];
+                else for (uint32_t k = t; k < stored; k += WV_THREADS) dst[out + k] = s[k];
                 if (adler_on && stored) adler_hbm(s, stored);
                 out += stored;
                 br.seek(br.pos + 8 * (uint64_t)stored);
@@ -777,9 +784,11 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                         }
                     }
                     // ---- E. emit: decode my share once more, write cells ----
-                    uint8_t* const wdst  = dst + out;                        // HBM address of wave offset 0
-                    const uint32_t shift = (uint32_t)((uintptr_t)wdst & 15); // slot of wave offset 0 (dst's 16-byte phase)
-                    const uint32_t reach = out >= WV_WINDOW ? 0x7fffffffu : (uint32_t)out;
+                    uint8_t* const wdst  = dst + (sym ? 2 * out : out);      // HBM address of wave offset 0
+                    // slot of wave offset 0: dst's phase inside a 16-element store unit (16 bytes, or 16 symbols = 32 bytes)
+                    const uint32_t shift = sym ? (uint32_t)((uintptr_t)wdst & 31) >> 1 : (uint32_t)((uintptr_t)wdst & 15);
+                    // a distance may reach `reach` bytes in front of the wave (a segment: always the whole 32 KiB window)
+                    const uint32_t reach = (sym || out >= WV_WINDOW) ? 0x7fffffffu : (uint32_t)out;
                     uint32_t emitted = 0, my_stop = 0xffffffffu, o = 0, from_staging = 0;
 #ifdef CL_NO_STAGING
                     kept = false;
@@ -902,8 +911,37 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                         WV_COUNT(4, rounds);
                     }
                     tick(7);
+                    // ---- G (segment). store: cells -> 16-bit symbols; a window cell takes the symbol stored at that position
+                    //      (byte or marker), or becomes a marker when the position lies in front of the segment ----
+                    if (sym && total) {
+                        uint16_t* const w16   = dst16 + out;                 // symbol address of wave offset 0
+                        uint16_t* const gbase = w16 - shift;                 // 32-byte aligned
+                        const uint32_t end    = shift + total;               // slots [shift, end) are ours
+                        auto cell_symbol = [&](uint32_t c) -> uint32_t {
+                            if (c < 256u) return c;
+                            const int64_t at = (int64_t)out + ((int32_t)c - (int32_t)CL_WINDOW_BIAS);   // position inside the segment
+                            return at >= 0 ? (uint32_t)dst16[at] : 0x8000u | (uint32_t)(at + (int64_t)WV_WINDOW);
+                        };
+                        const uint32_t qlo = (shift + 15) >> 4, qhi = end >> 4;       // chunks [qlo, qhi) are whole
+                        for (uint32_t c = qlo + t; c < qhi; c += WV_THREADS) {
+                            const uint4 h0 = *reinterpret_cast<const uint4*>(sh.cells + (c << 4));
+                            const uint4 h1 = *reinterpret_cast<const uint4*>(sh.cells + (c << 4) + 8);
+                            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                            uint32_t v[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = cell_symbol(hw[q] & 0xffffu) | cell_symbol(hw[q] >> 16) << 16;
+                            uint4* const g = reinterpret_cast<uint4*>(gbase + (c << 4));
+                            g[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                            g[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                        }
+                        if (t < 2) {   // the ragged head and tail (at most 15 symbols each)
+                            const uint32_t k0 = t == 0 ? shift : max(qhi << 4, shift), k1 = t == 0 ? min(qlo << 4, end) : end;
+                            const bool     skip = t == 1 && qhi < qlo;
+                            for (uint32_t k = k0; k < k1 && !skip; ++k) gbase[k] = (uint16_t)cell_symbol(sh.cells[k]);
+                        }
+                    }
                     // ---- G. store: cells -> bytes (window cells gathered from the stream's own output), 16-byte coalesced ----
-                    if (total) {
+                    if (!sym && total) {
                         uint8_t* const gbase = wdst - shift;                 // 16-byte aligned
                         const uint32_t end   = shift + total;                // slots [shift, end) are ours
                         const uint32_t nq    = (end + 15) >> 4;
@@ -993,6 +1031,7 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
             ++blocks;
             resume_bit = br.at();
             resume_out = out;
+            if (job.stop_bit && !final && br.at() >= job.stop_bit) break;   // end of my segment (the host checks ==)
             if (final) {
                 phase = 2;
                 st = read_trailer(br, job.format, r);
@@ -1037,7 +1076,15 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                 for (int k = 0; k < 12; ++k) r->stat_cycles[k] = sh.cyc[k];
             }
         }
-        if (fallback) {
+        if (fallback && sym) {
+            // a segment cannot go through the byte-wise serial decoder: report it, the host decodes the stream whole
+            if (t == 0) {
+                r->status = PNGB200_ERR_INTERNAL;
+                r->produced = out;
+                r->consumed_bits = br.at();
+                r->blocks = blocks;
+            }
+        } else if (fallback) {
             __syncthreads();
             if (warp == 0) serial_inflate(sh.ser, job, r, resume_bit, resume_out, 1, blocks);
         } else if (t == 0) {

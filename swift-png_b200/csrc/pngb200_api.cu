@@ -98,6 +98,8 @@ struct pngb200_ctx {
     int          inflate_mode = 0;
     int          last_engine = -1;       // whole-stream engine of the last batch: 0 round-1, 1 ring, 2 cells, -1 none
     bool         cells_auto = false;     // automatic mode may pick inflate_cells_kernel (set once measured faster)
+    bool         cells_segments = true;  // segments (several CTAs per stream) are decoded by inflate_cells_kernel: 3 CTA slots per SM instead
+                                         // of 2 (r02b: 8 x 8K RGBA8 6 143 -> 7 089 MPixels/s; PNGB200_CELLS_SEGMENTS=0 restores the ring kernel)
     int          sm_count = 148;
     std::string  error;
     bool         pending = false;
@@ -182,7 +184,7 @@ int ensure_crc_tables(pngb200_ctx* ctx)
 int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t>& par)
 {
     ctx->seg_streams = ctx->seg_segments = ctx->seg_fallbacks = 0;
-    const size_t slots = (size_t)ctx->sm_count * WV_CTAS_PER_SM;
+    const size_t slots = (size_t)ctx->sm_count * (ctx->cells_segments ? CL_CTAS_PER_SM : WV_CTAS_PER_SM);
     constexpr uint64_t kMinSegment = 256u << 10;  // compressed bytes per segment, at least
     if (par.empty() || par.size() * 2 > slots) return PNGB200_OK;
     const size_t per_stream = std::max<size_t>(1, slots / par.size());
@@ -257,8 +259,8 @@ int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t
     CU(cudaMemsetAsync(ctx->d_sgres.p, 0, sizeof(StreamResult) * n, ctx->stream));
     {
         WvParams pp;
-        pp.bitmap_words = wv_bitmap_words(max_cap);
-        pp.scratch_stride = wv_scratch_stride(pp.bitmap_words);
+        pp.bitmap_words = ctx->cells_segments ? 8 : wv_bitmap_words(max_cap);
+        pp.scratch_stride = ctx->cells_segments ? CL_SCRATCH : wv_scratch_stride(pp.bitmap_words);
         unsigned grid = (unsigned)std::min<size_t>(n, slots);
         size_t need = (size_t)pp.scratch_stride * grid + 256;
         if (need > ctx->d_scratch.cap || pp.scratch_stride != ctx->scratch_stride) {
@@ -273,7 +275,8 @@ int run_segments(pngb200_ctx* ctx, const StreamJob* h_jobs, std::vector<uint32_t
         pp.order = nullptr;
         pp.scratch = ctx->d_scratch.as<uint8_t>();
         pp.count = (int)n;
-        inflate_wave_kernel<<<grid, WV_THREADS, sizeof(WvShared), ctx->stream>>>(pp);
+        if (ctx->cells_segments) inflate_cells_kernel<<<grid, WV_THREADS, sizeof(ClShared), ctx->stream>>>(pp);
+        else inflate_wave_kernel<<<grid, WV_THREADS, sizeof(WvShared), ctx->stream>>>(pp);
         ctx->launches++;
     }
     CU(cudaMemcpyAsync(ctx->h_sgres.p, ctx->d_sgres.p, sizeof(StreamResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -766,6 +769,7 @@ int run_over_lanes(pngb200_ctx* ctx, size_t count, int memspace, BytesOf bytes_o
             pngb200_ctx* lane = ctx->lanes[l];
             lane->inflate_mode = ctx->inflate_mode;
             lane->cells_auto = ctx->cells_auto;
+            lane->cells_segments = ctx->cells_segments;
             lane->parallel_threshold = ctx->parallel_threshold;
             lane->peer_streams = count;
             for (size_t c = l; c < nchunks; c += kLanes) {
@@ -830,7 +834,8 @@ pngb200_ctx* pngb200_ctx_create(int device)
     pngb200_ctx* ctx = new pngb200_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* v = getenv("PNGB200_CELLS_AUTO")) ctx->cells_auto = atoi(v) != 0;   // tuning override, read once per context
+    if (const char* v = getenv("PNGB200_CELLS_AUTO")) ctx->cells_auto = atoi(v) != 0;   // tuning overrides, read once per context
+    if (const char* v = getenv("PNGB200_CELLS_SEGMENTS")) ctx->cells_segments = atoi(v) != 0;
     DeviceGuard guard(device);
     if (cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DfShared)) != cudaSuccess) {
         set_error(nullptr, PNGB200_ERR_CUDA, "cannot opt in to %zu bytes of shared memory", sizeof(DfShared));

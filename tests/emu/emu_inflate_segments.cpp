@@ -5,6 +5,9 @@
 #include "../../swift-png_b200/csrc/inflate_wave.cuh"
 #include "../../swift-png_b200/csrc/block_search.cuh"
 #include "../../swift-png_b200/csrc/inflate_segments.cuh"
+#ifdef EMU_SEG_CELLS
+#include "../../swift-png_b200/csrc/inflate_cells.cuh"
+#endif
 
 using namespace pngb200;
 
@@ -43,12 +46,19 @@ extern "C" int emu_inflate_segmented(const uint8_t* src, uint64_t len, uint8_t* 
     uint32_t ticket = 0;
     WvParams P{};
     P.jobs = sg.data(); P.results = sr.data(); P.order = nullptr; P.ticket = &ticket; P.count = (int)n;
+    const unsigned grid = (unsigned)std::min<size_t>(n, 3);   // fewer CTAs than segments: the ticket loop is exercised
+#ifdef EMU_SEG_CELLS
+    P.scratch_stride = CL_SCRATCH;
+    std::vector<uint8_t> scratch(P.scratch_stride * grid + 256, 0);
+    P.scratch = scratch.data();
+    simt::launch(grid, WV_THREADS, sizeof(ClShared), [&]() { inflate_cells_kernel(P); });
+#else
     P.bitmap_words = wv_bitmap_words(max_cap);
     P.scratch_stride = wv_scratch_stride(P.bitmap_words);
-    const unsigned grid = (unsigned)std::min<size_t>(n, 3);   // fewer CTAs than segments: the ticket loop is exercised
     std::vector<uint8_t> scratch(P.scratch_stride * grid + 256, 0);
     P.scratch = scratch.data();
     simt::launch(grid, WV_THREADS, sizeof(WvShared), [&]() { inflate_wave_kernel(P); });
+#endif
     *segments_used = (uint32_t)n;
     bool ok = true;
     uint64_t total = 0;
