@@ -853,6 +853,7 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                     }
                     WV_COUNT(2, emitted);
                     WV_COUNT(3, from_staging);
+                    (void)from_staging;   // (cost-model counter of emulator builds)
                     if (cut && my_stop != 0xffffffffu) atomicMin(&sh.cut_pos, my_stop);
                     __syncthreads();                                      // (7) cells written
                     tick(6);
@@ -944,7 +945,6 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                     if (!sym && total) {
                         uint8_t* const gbase = wdst - shift;                 // 16-byte aligned
                         const uint32_t end   = shift + total;                // slots [shift, end) are ours
-                        const uint32_t nq    = (end + 15) >> 4;
                         uint32_t a = 0, bw = 0;
                         auto cell_byte = [&](uint32_t c) -> uint32_t {
                             // a window cell: relative position c - 0x8100 in [-32768, -1]
