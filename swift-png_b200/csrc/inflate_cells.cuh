@@ -789,7 +789,8 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                     const uint32_t shift = sym ? (uint32_t)((uintptr_t)wdst & 31) >> 1 : (uint32_t)((uintptr_t)wdst & 15);
                     // a distance may reach `reach` bytes in front of the wave (a segment: always the whole 32 KiB window)
                     const uint32_t reach = (sym || out >= WV_WINDOW) ? 0x7fffffffu : (uint32_t)out;
-                    uint32_t emitted = 0, my_stop = 0xffffffffu, o = 0, from_staging = 0;
+                    uint32_t emitted = 0, my_stop = 0xffffffffu, o = 0;
+                    [[maybe_unused]] uint32_t from_staging = 0;   // (cost-model counter of emulator builds)
 #ifdef CL_NO_STAGING
                     kept = false;
 #endif
@@ -853,7 +854,6 @@ __global__ void __launch_bounds__(WV_THREADS, CL_CTAS_PER_SM) inflate_cells_kern
                     }
                     WV_COUNT(2, emitted);
                     WV_COUNT(3, from_staging);
-                    (void)from_staging;   // (cost-model counter of emulator builds)
                     if (cut && my_stop != 0xffffffffu) atomicMin(&sh.cut_pos, my_stop);
                     __syncthreads();                                      // (7) cells written
                     tick(6);
